@@ -1,0 +1,861 @@
+// K2: one outer iteration of the bundle-entropy method for every unfinished sample.
+//
+// Restates on the GPU the per-sample loop body of the reference's three solveBatch copies
+// (paths under /root/reference):
+//   lib/bundle_entropy.py:211-237        append row, SVD rank stop, pdipm_pc (:5-78), prune lam<=1e-8
+//   lib/bundle_entropy_dual.py:148-174   append, rank stop, proj_newton_logistic (:15-85), prune lam<=0
+//   RL/src/bundle_entropy.py:106-131     append, Newton (:14-83), clip [.03,.97], |dy|<1e-6 stop
+//
+// Work decomposition: a GROUP of WPS warps owns one sample (WPS = 1 for small n_y: eight samples
+// per CTA; WPS = 8: one CTA per sample).  Bundle rows G_j (float32, written by K1 straight into
+// the sample's free slot) are streamed coalesced along n_y; every reduction over n_y is
+// accumulated in FP64, the k x k algebra (k <= KS) is FP64 in shared memory and is executed by
+// warp 0 of the group.  Three access patterns cover every variant:
+//   column pass : thread owns columns e, loops rows j      ->  n-vector  = G^T w      (k loads/col)
+//   row pass    : warp owns rows j, lanes stride columns   ->  k-vector  = G v       (shuffle reduce)
+//   gram pass   : warp owns 4x4 blocks of the k x k output ->  G diag(w) G^T         (shuffle reduce)
+#include "common.cuh"
+
+namespace icnn {
+
+struct StepArgs {
+  icnn_bundle_bufs b;
+  icnn_bundle_cfg c;
+  int t;
+  int npad;  // doubles reserved per n-vector in shared memory
+  int ld;    // leading dimension of the k x k matrices
+};
+
+constexpr int NKVEC = 20;  // k-vectors per group in shared memory
+
+__host__ __device__ inline size_t group_smem_doubles(int npad, int KS, int ld, int wps) {
+  // 3 n-vectors, 2 matrices, NKVEC k-vectors, reduction scratch, scalars
+  return (size_t)3 * npad + (size_t)2 * KS * ld + (size_t)NKVEC * KS + 4 * wps + 16;
+}
+
+template <int WPS>
+struct Grp {
+  int tid, lane, warp, gid;
+  double* red;  // [4*WPS]
+  static constexpr int T = WPS * 32;
+
+  __device__ __forceinline__ void sync() const {
+    if (WPS == 1) __syncwarp();
+    else if (WPS == 8) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(WPS * 32) : "memory");
+  }
+  static __device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  static __device__ __forceinline__ double wmin(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  }
+  static __device__ __forceinline__ double wmax(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  }
+  // all-reduce over the group; every thread gets the result
+  __device__ __forceinline__ double sum(double v) const {
+    v = wsum(v);
+    if (WPS == 1) return v;
+    if (lane == 0) red[warp] = v;
+    sync();
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < WPS; ++w) r += red[w];
+    sync();
+    return r;
+  }
+  __device__ __forceinline__ double min(double v) const {
+    v = wmin(v);
+    if (WPS == 1) return v;
+    if (lane == 0) red[warp] = v;
+    sync();
+    double r = red[0];
+#pragma unroll
+    for (int w = 1; w < WPS; ++w) r = fmin(r, red[w]);
+    sync();
+    return r;
+  }
+  __device__ __forceinline__ double max(double v) const {
+    v = wmax(v);
+    if (WPS == 1) return v;
+    if (lane == 0) red[warp] = v;
+    sync();
+    double r = red[0];
+#pragma unroll
+    for (int w = 1; w < WPS; ++w) r = fmax(r, red[w]);
+    sync();
+    return r;
+  }
+};
+
+// ---- k x k dense algebra, executed by ONE warp (lane-parallel over rows), FP64 in smem -------
+
+// In-place lower Cholesky of the symmetric matrix A (full storage, leading dim ld).
+// Returns false on a non-positive / non-finite pivot.  minpiv (optional) gets the last pivot.
+__device__ inline bool warp_cholesky(double* A, int k, int ld, int lane, double* last_pivot) {
+  bool ok = true;
+  for (int c = 0; c < k; ++c) {
+    // s_r = A[r][c] - sum_{p<c} L[r][p] L[c][p]   for r >= c
+    for (int r = c + lane; r < k; r += 32) {
+      double s = A[r * ld + c];
+      for (int p = 0; p < c; ++p) s -= A[r * ld + p] * A[c * ld + p];
+      A[r * ld + c] = s;
+    }
+    __syncwarp();
+    const double piv = A[c * ld + c];
+    if (c == k - 1 && last_pivot) *last_pivot = piv;
+    if (!(piv > 0.0) || !isfinite(piv)) { ok = false; break; }
+    const double d = sqrt(piv);
+    __syncwarp();
+    for (int r = c + lane; r < k; r += 32) A[r * ld + c] = (r == c) ? d : A[r * ld + c] / d;
+    __syncwarp();
+  }
+  __syncwarp();
+  return ok;
+}
+
+// Solve L L^T x = b in place (b -> x), L lower from warp_cholesky.  One warp.
+__device__ inline void warp_chol_solve(const double* L, int k, int ld, double* b, int lane) {
+  for (int i = 0; i < k; ++i) {  // forward
+    const double xi = b[i] / L[i * ld + i];
+    __syncwarp();
+    for (int r = i + 1 + lane; r < k; r += 32) b[r] -= L[r * ld + i] * xi;
+    if (lane == 0) b[i] = xi;
+    __syncwarp();
+  }
+  for (int i = k - 1; i >= 0; --i) {  // backward with L^T
+    const double xi = b[i] / L[i * ld + i];
+    __syncwarp();
+    for (int r = lane; r < i; r += 32) b[r] -= L[i * ld + r] * xi;
+    if (lane == 0) b[i] = xi;
+    __syncwarp();
+  }
+}
+
+// step length keeping v + a dv >= 0  (lib/bundle_entropy.py:158-163), over a k-vector, one warp
+__device__ inline double warp_max_step(const double* v, const double* dv, int k, int lane) {
+  double a = 1e300;
+  bool any = false;
+  for (int j = lane; j < k; j += 32)
+    if (dv[j] < 0.0) { a = fmin(a, -v[j] / dv[j]); any = true; }
+  a = Grp<1>::wmin(a);
+  any = __any_sync(0xffffffffu, any);
+  return any ? a : 1.0;
+}
+
+__device__ __forceinline__ double softplus_d(double x) {  // lib/bundle_entropy_dual.py:6-12
+  return x > 1.0 ? log1p(exp(-x)) + x : log1p(exp(x));
+}
+
+// ---- G passes -----------------------------------------------------------------------------
+
+// gram pass: M[i][j] = sum_e w[e] G_i[e] G_j[e] (symmetric fill), w == nullptr -> 1
+template <int WPS>
+__device__ inline void gram_pass(const Grp<WPS>& g, const float* const* rowp, int k, int n,
+                                 const double* w, double* M, int ld) {
+  const int kb = (k + 3) >> 2;
+  const int nblk = kb * (kb + 1) / 2;
+  for (int blk = g.warp; blk < nblk; blk += WPS) {
+    // unrank blk -> (bi <= bj)
+    int bi = 0, rem = blk;
+    while (rem >= kb - bi) { rem -= kb - bi; ++bi; }
+    const int bj = bi + rem;
+    const float* ri[4];
+    const float* rj[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      ri[a] = rowp[min(bi * 4 + a, k - 1)];
+      rj[a] = rowp[min(bj * 4 + a, k - 1)];
+    }
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int e = g.lane; e < n; e += 32) {
+      const double we = w ? w[e] : 1.0;
+      double vi[4], vj[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { vi[a] = (double)__ldg(ri[a] + e) * we; vj[a] = (double)__ldg(rj[a] + e); }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fma(vi[a], vj[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const double v = Grp<WPS>::wsum(acc[a][b]);
+        const int i = bi * 4 + a, j = bj * 4 + b;
+        if (g.lane == 0 && i < k && j < k) { M[i * ld + j] = v; M[j * ld + i] = v; }
+      }
+  }
+}
+
+// ---- the step kernel ----------------------------------------------------------------------
+
+template <int WPS>
+__global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
+  const icnn_bundle_bufs& b = A.b;
+  const icnn_bundle_cfg& cf = A.c;
+  if (b.nactive[A.t] == 0) return;
+  extern __shared__ double smem_d[];
+  constexpr int GPB = 8 / WPS;  // groups per block
+  Grp<WPS> g;
+  g.tid = threadIdx.x % (WPS * 32);
+  g.lane = threadIdx.x & 31;
+  g.warp = g.tid >> 5;
+  g.gid = threadIdx.x / (WPS * 32);
+  const int u = blockIdx.x * GPB + g.gid;
+  if (u >= b.B) return;
+  if (b.finished[u]) return;
+
+  const int n = b.n, KS = b.KS, ld = A.ld, npad = A.npad;
+  double* base = smem_d + (size_t)g.gid * group_smem_doubles(npad, KS, ld, WPS);
+  double* yv = base;            // n-vectors
+  double* rv = yv + npad;
+  double* dv = rv + npad;
+  double* M = dv + npad;        // k x k
+  double* Lm = M + (size_t)KS * ld;
+  double* kv = Lm + (size_t)KS * ld;
+  double* hk = kv + 0 * KS;     // offsets h_j (logical order)
+  double* zk = kv + 1 * KS;     // lambda / z
+  double* sk = kv + 2 * KS;
+  double* rdk = kv + 3 * KS;
+  double* qk = kv + 4 * KS;
+  double* rk = kv + 5 * KS;
+  double* dza = kv + 6 * KS;
+  double* dsa = kv + 7 * KS;
+  double* dzc = kv + 8 * KS;
+  double* dsc = kv + 9 * KS;
+  double* w1 = kv + 10 * KS;
+  double* ck = kv + 11 * KS;
+  double* gk = kv + 12 * KS;   // gradient
+  double* g0 = kv + 13 * KS;
+  double* dk = kv + 14 * KS;   // Newton direction
+  double* lnk = kv + 15 * KS;  // trial lambda
+  double* yk = kv + 16 * KS;   // change of variables y (lambda with pivot set to 1)
+  double* ek = kv + 17 * KS;   // e vector
+  double* tk = kv + 18 * KS;   // temp
+  const float** rowp = reinterpret_cast<const float**>(kv + 19 * KS);  // row pointers (k+1 <= KS)
+  g.red = kv + (size_t)NKVEC * KS;
+  double* sc = g.red + 4 * WPS;  // 16 scalars
+  int* isc = reinterpret_cast<int*>(sc + 12);  // 8 ints
+
+  const int k0 = b.count[u];
+  const int k = k0 + 1;
+  const int* permu = b.perm + (size_t)u * KS;
+  float* Gu = b.G + (size_t)u * KS * n;
+  double* hu = b.h + (size_t)u * KS;
+  double* lamu = b.lam + (size_t)u * KS;
+  double* rsu = b.rsum + (size_t)u * KS;
+  double* gramu = b.gram + (size_t)u * KS * KS;
+  double* yu = b.y + (size_t)u * n;
+  const int slot_new = permu[k0];
+
+  for (int j = g.tid; j < k; j += g.T) rowp[j] = Gu + (size_t)permu[j] * n;
+  if (g.tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) isc[i] = 0;
+  }
+  g.sync();
+  const float* gnew = rowp[k0];
+
+  // ---- append: h = f - g.y ; row sum ; unweighted Gram row ; xs copy ; non-finite guard ------
+  {
+    double hs = 0.0, rs = 0.0, bad = 0.0;
+    double* ysrow = b.ys ? b.ys + ((size_t)u * KS + slot_new) * n : nullptr;
+    for (int e = g.tid; e < n; e += g.T) {
+      const double ge = (double)gnew[e];
+      const double ye = yu[e];
+      yv[e] = ye;
+      hs = fma(ge, ye, hs);
+      rs += ge;
+      if (!isfinite(ge)) bad = 1.0;
+      if (ysrow) ysrow[e] = ye;
+    }
+    hs = g.sum(hs);
+    rs = g.sum(rs);
+    bad = g.max(bad);
+    const double fu = (double)b.f[u];
+    if (bad > 0.0 || !isfinite(fu)) {
+      if (g.tid == 0) { b.status[u] = ICNN_ST_NONFINITE; b.finished[u] = 1; b.nIters[u] = A.t - 1; }
+      return;
+    }
+    // Gram row of the new row against all active rows (row pass), plus exact-duplicate detection
+    for (int j = g.warp; j < k; j += WPS) {
+      const float* rj = rowp[j];
+      double acc = 0.0;
+      int diff = 0;
+      for (int e = g.lane; e < n; e += 32) {
+        const float a = __ldg(rj + e), c = gnew[e];
+        acc = fma((double)a, (double)c, acc);
+        diff |= (a != c);
+      }
+      acc = Grp<WPS>::wsum(acc);
+      diff = __any_sync(0xffffffffu, diff);
+      if (g.lane == 0) { tk[j] = acc; if (j < k0 && !diff) isc[0] = 1; }
+    }
+    if (g.tid == 0) { hu[slot_new] = fu - hs; rsu[slot_new] = rs; }
+    g.sync();
+  }
+  // NOTE: control flow below is group-uniform: every decision is read from shared memory after
+  // a group barrier.
+  bool dependent = false;
+  if (cf.variant != ICNN_VARIANT_RL) {
+    // ---- dependency test (stands in for np.linalg.matrix_rank, lib/bundle_entropy.py:219) ----
+    // distance of the new row from the span of the active rows, computed explicitly with one
+    // step of iterative refinement, relative to the largest row norm.
+    if (k > n) dependent = true;
+    else if (k0 > 0) {
+      if (g.warp == 0) {
+        for (int i = g.lane; i < k0; i += 32)
+          for (int j = 0; j < k0; ++j) Lm[i * ld + j] = gramu[(size_t)permu[i] * KS + permu[j]];
+        for (int j = g.lane; j < k0; j += 32) { rk[j] = tk[j]; }
+        __syncwarp();
+        const bool ok = warp_cholesky(Lm, k0, ld, g.lane, nullptr);
+        if (ok) warp_chol_solve(Lm, k0, ld, rk, g.lane);
+        if (g.lane == 0) isc[1] = ok ? 1 : 0;
+        __syncwarp();
+      }
+      g.sync();
+      double maxdiag = tk[k0];
+      for (int j = 0; j < k0; ++j) maxdiag = fmax(maxdiag, gramu[(size_t)permu[j] * KS + permu[j]]);
+      if (isc[0]) dependent = true;          // exact duplicate of an active row
+      else if (!isc[1]) dependent = true;    // active rows themselves numerically dependent
+      else {
+        const double thr2 = cf.rank_tol * cf.rank_tol * maxdiag;
+        for (int rep = 0; rep < 2; ++rep) {
+          // residual res = (rep ? res : gnew) - sum_j c_j G_j
+          double p = 0.0;
+          for (int e = g.tid; e < n; e += g.T) {
+            double r = rep ? rv[e] : (double)gnew[e];
+            for (int j = 0; j < k0; ++j) r = fma(-rk[j], (double)__ldg(rowp[j] + e), r);
+            rv[e] = r;
+            p = fma(r, r, p);
+          }
+          p = g.sum(p);
+          if (p <= thr2) { dependent = true; break; }
+          // clearly independent (relative distance > 1e-4), or already refined once
+          if (rep == 1 || p > 1e-8 * maxdiag) break;
+          // gray zone: one step of iterative refinement, c' = M^-1 (G res)
+          g.sync();
+          for (int j = g.warp; j < k0; j += WPS) {
+            double acc = 0.0;
+            for (int e = g.lane; e < n; e += 32) acc = fma((double)__ldg(rowp[j] + e), rv[e], acc);
+            acc = Grp<WPS>::wsum(acc);
+            if (g.lane == 0) rk[j] = acc;
+          }
+          g.sync();
+          if (g.warp == 0) warp_chol_solve(Lm, k0, ld, rk, g.lane);
+          g.sync();
+        }
+      }
+    } else {
+      dependent = !(tk[0] > 0.0);  // a zero first row has rank 0 < 1
+    }
+    if (dependent) {
+      // pop the row, mark finished, nIters = t-1 (lib/bundle_entropy.py:220-225); y unchanged
+      if (g.tid == 0) { b.status[u] = ICNN_ST_RANK_STOP; b.finished[u] = 1; b.nIters[u] = A.t - 1; }
+      return;
+    }
+  }
+  // commit the Gram row
+  for (int j = g.tid; j < k; j += g.T) {
+    gramu[(size_t)slot_new * KS + permu[j]] = tk[j];
+    gramu[(size_t)permu[j] * KS + slot_new] = tk[j];
+  }
+  for (int j = g.tid; j < k; j += g.T) hk[j] = hu[permu[j]];  // permu[k0] == slot_new
+  g.sync();
+
+  int inner_its = 0;
+  int fail = 0;
+
+  if (cf.solver == ICNN_SOLVER_PC) {
+    // =====================  Mehrotra predictor-corrector, lib/bundle_entropy.py:5-78  ==========
+    const int maxit = cf.max_inner > 0 ? cf.max_inner : 20;
+    for (int e = g.tid; e < n; e += g.T) yv[e] = 0.5;
+    for (int j = g.tid; j < k; j += g.T) { zk[j] = 1.0 / k; sk[j] = 1.0; }
+    if (g.tid == 0) sc[0] = 1.0;  // t
+    g.sync();
+    for (int it = 0; it < maxit; ++it) {
+      // column pass: ry = log y - log(1-y) + G^T z
+      double pr = 0.0;
+      for (int e = g.tid; e < n; e += g.T) {
+        double a = 0.0;
+        for (int j = 0; j < k; ++j) a = fma((double)__ldg(rowp[j] + e), zk[j], a);
+        const double ye = yv[e];
+        const double r = log(ye) - log(1.0 - ye) + a;
+        rv[e] = r;
+        pr = fma(r, r, pr);
+      }
+      pr = g.sum(pr);
+      // row pass: rd = G y + h - t + s ; q = G D ry     (D = y(1-y) = 1/(1/y + 1/(1-y)))
+      for (int j = g.warp; j < k; j += WPS) {
+        const float* rj = rowp[j];
+        double a1 = 0.0, a2 = 0.0;
+        for (int e = g.lane; e < n; e += 32) {
+          const double ge = (double)__ldg(rj + e), ye = yv[e];
+          a1 = fma(ge, ye, a1);
+          a2 = fma(ge, ye * (1.0 - ye) * rv[e], a2);
+        }
+        a1 = Grp<WPS>::wsum(a1);
+        a2 = Grp<WPS>::wsum(a2);
+        if (g.lane == 0) { rdk[j] = a1 + hk[j] - sc[0] + sk[j]; qk[j] = a2; }
+      }
+      g.sync();
+      if (g.warp == 0) {
+        double zs = 0.0, dr = 0.0;
+        for (int j = g.lane; j < k; j += 32) { zs += zk[j]; dr = fma(rdk[j], rdk[j], dr); }
+        zs = Grp<1>::wsum(zs);
+        dr = Grp<1>::wsum(dr);
+        const double rt = 1.0 - zs;
+        if (g.lane == 0) {
+          sc[1] = rt;
+          isc[2] = (sqrt(pr + rt * rt) < 1e-8 && sqrt(dr) < 1e-8) ? 1 : 0;
+        }
+      }
+      g.sync();
+      if (isc[2]) break;
+      inner_its = it + 1;
+      // weights D into dv, then the weighted Gram
+      for (int e = g.tid; e < n; e += g.T) { const double ye = yv[e]; dv[e] = ye * (1.0 - ye); }
+      g.sync();
+      gram_pass<WPS>(g, rowp, k, n, dv, M, ld);
+      g.sync();
+      if (g.warp == 0) {
+        const int lane = g.lane;
+        for (int j = lane; j < k; j += 32) M[j * ld + j] += sk[j] / zk[j];
+        __syncwarp();
+        for (int i = lane; i < k; i += 32)
+          for (int j = 0; j < k; ++j) Lm[i * ld + j] = M[i * ld + j];
+        __syncwarp();
+        const bool ok = warp_cholesky(Lm, k, ld, lane, nullptr);
+        if (!ok) { if (lane == 0) isc[3] = 1; }
+        else {
+          if (lane == 0) isc[3] = 0;
+          for (int j = lane; j < k; j += 32) w1[j] = 1.0;
+          __syncwarp();
+          warp_chol_solve(Lm, k, ld, w1, lane);
+          double w1s = 0.0;
+          for (int j = lane; j < k; j += 32) w1s += w1[j];
+          w1s = Grp<1>::wsum(w1s);
+          // affine: r = rd - G D ry - (s/z) rc, rc = z  ->  r = rd - q - s
+          double rw = 0.0;
+          for (int j = lane; j < k; j += 32) { rk[j] = rdk[j] - qk[j] - sk[j]; rw = fma(rk[j], w1[j], rw); }
+          rw = Grp<1>::wsum(rw);
+          const double dt = (rw - sc[1]) / w1s;
+          for (int j = lane; j < k; j += 32) dza[j] = rk[j] - dt;
+          __syncwarp();
+          warp_chol_solve(Lm, k, ld, dza, lane);
+          for (int j = lane; j < k; j += 32) dsa[j] = -(sk[j] / zk[j]) * (zk[j] + dza[j]);
+          if (lane == 0) { sc[2] = dt; sc[3] = w1s; }
+          __syncwarp();
+        }
+      }
+      g.sync();
+      if (isc[3]) { fail = 1; break; }
+      // column pass: dy_aff = -D (ry + G^T dz_aff) ; get_step(y, dy) and get_step(1-y, -dy)
+      double st = 1e300, st2 = 1e300;
+      for (int e = g.tid; e < n; e += g.T) {
+        double a = 0.0;
+        for (int j = 0; j < k; ++j) a = fma((double)__ldg(rowp[j] + e), dza[j], a);
+        const double dy = -dv[e] * (rv[e] + a);
+        rv[e] = dy;  // rv now holds dy_aff
+        const double ye = yv[e];
+        if (dy < 0.0) st = fmin(st, -ye / dy);
+        if (dy > 0.0) st2 = fmin(st2, (1.0 - ye) / dy);
+      }
+      st = g.min(st);
+      st2 = g.min(st2);
+      st = fmin(st > 1e299 ? 1.0 : st, st2 > 1e299 ? 1.0 : st2);
+      if (g.warp == 0) {
+        const int lane = g.lane;
+        double alpha = fmin(fmin(warp_max_step(zk, dza, k, lane), warp_max_step(sk, dsa, k, lane)),
+                            fmin(st, 1.0));
+        double num = 0.0, den = 0.0;
+        for (int j = lane; j < k; j += 32) {
+          num = fma(sk[j] + alpha * dsa[j], zk[j] + alpha * dza[j], num);
+          den = fma(sk[j], zk[j], den);
+        }
+        num = Grp<1>::wsum(num);
+        den = Grp<1>::wsum(den);
+        const double sg = num / den;
+        const double sig = sg * sg * sg;
+        const double mu = den / k;
+        // corrector: ry = rt = rd = 0, rc = -(mu sig - ds_aff dz_aff)/s  ->  r = -(s/z) rc
+        double rw = 0.0;
+        for (int j = lane; j < k; j += 32) {
+          const double rc = -(mu * sig - dsa[j] * dza[j]) / sk[j];
+          tk[j] = rc;
+          rk[j] = -(sk[j] / zk[j]) * rc;
+          rw = fma(rk[j], w1[j], rw);
+        }
+        rw = Grp<1>::wsum(rw);
+        const double dtc = rw / sc[3];
+        for (int j = lane; j < k; j += 32) dzc[j] = rk[j] - dtc;
+        __syncwarp();
+        warp_chol_solve(Lm, k, ld, dzc, lane);
+        for (int j = lane; j < k; j += 32) {
+          dsc[j] = -(sk[j] / zk[j]) * (tk[j] + dzc[j]);
+          dza[j] += dzc[j];   // total dz
+          dsa[j] += dsc[j];   // total ds
+        }
+        if (lane == 0) sc[2] += dtc;  // total dt
+        __syncwarp();
+      }
+      g.sync();
+      // column pass: dy = dy_aff - D G^T dz_cor ; step bounds
+      st = 1e300; st2 = 1e300;
+      for (int e = g.tid; e < n; e += g.T) {
+        double a = 0.0;
+        for (int j = 0; j < k; ++j) a = fma((double)__ldg(rowp[j] + e), dzc[j], a);
+        const double dy = rv[e] - dv[e] * a;
+        rv[e] = dy;
+        const double ye = yv[e];
+        if (dy < 0.0) st = fmin(st, -ye / dy);
+        if (dy > 0.0) st2 = fmin(st2, (1.0 - ye) / dy);
+      }
+      st = g.min(st);
+      st2 = g.min(st2);
+      st = fmin(st > 1e299 ? 1.0 : st, st2 > 1e299 ? 1.0 : st2);
+      if (g.warp == 0) {
+        const int lane = g.lane;
+        double a = fmin(fmin(warp_max_step(sk, dsa, k, lane), warp_max_step(zk, dza, k, lane)), st);
+        a = fmax(0.0, fmin(1.0, 0.99 * a));
+        for (int j = lane; j < k; j += 32) { sk[j] += a * dsa[j]; zk[j] += a * dza[j]; }
+        if (lane == 0) { sc[0] += a * sc[2]; sc[4] = a; }
+        __syncwarp();
+      }
+      g.sync();
+      const double a = sc[4];
+      for (int e = g.tid; e < n; e += g.T) yv[e] += a * rv[e];
+      g.sync();
+    }
+  } else {
+    // =====================  dual projected Newton  ============================================
+    // lib/bundle_entropy_dual.py:15-85 ; RL deltas RL/src/bundle_entropy.py:14-83
+    const bool rl = (cf.variant == ICNN_VARIANT_RL);
+    const int maxit = cf.max_inner > 0 ? cf.max_inner : (rl ? 20 : 100);
+    const int maxback = rl ? 10 : 50;
+    if (k == 1) {
+      if (g.tid == 0) zk[0] = 1.0;  // lam = [1]  (:166-168)
+      g.sync();
+    } else {
+      for (int j = g.tid; j < k; j += g.T) { zk[j] = 1.0 / k; ck[j] = rsu[permu[j]] + hk[j]; ek[j] = 1.0; }
+      g.sync();
+      bool done = false;
+      for (int it = 0; it < maxit && !done; ++it) {
+        inner_its = it + 1;
+        // column pass: a = G^T lam ; z = sigma(a) ; F = -c.lam + sum softplus(a)
+        double fs = 0.0;
+        for (int e = g.tid; e < n; e += g.T) {
+          double a = 0.0;
+          for (int j = 0; j < k; ++j) a = fma((double)__ldg(rowp[j] + e), zk[j], a);
+          const double ze = 1.0 / (1.0 + exp(-a));
+          yv[e] = ze;
+          dv[e] = ze * (1.0 - ze);
+          fs += softplus_d(a);
+        }
+        fs = g.sum(fs);
+        // row pass: grad = -c + G z
+        for (int j = g.warp; j < k; j += WPS) {
+          const float* rj = rowp[j];
+          double acc = 0.0;
+          for (int e = g.lane; e < n; e += 32) acc = fma((double)__ldg(rj + e), yv[e], acc);
+          acc = Grp<WPS>::wsum(acc);
+          if (g.lane == 0) gk[j] = acc - ck[j];
+        }
+        gram_pass<WPS>(g, rowp, k, n, dv, M, ld);
+        g.sync();
+        if (g.warp == 0) {
+          const int lane = g.lane;
+          // F, pivot p = argmax lam (first maximum, np.argmax)
+          double cl = 0.0;
+          for (int j = lane; j < k; j += 32) cl = fma(ck[j], zk[j], cl);
+          cl = Grp<1>::wsum(cl);
+          const double F = fs - cl;
+          double best = -1e300; int bi = 0;
+          for (int j = lane; j < k; j += 32) if (zk[j] > best) { best = zk[j]; bi = j; }
+          for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+          }
+          const int p = bi;
+          // change of variables, reduced gradient / Hessian, bound set
+          int nfree = 0;
+          double gn = 0.0;
+          for (int j = lane; j < k; j += 32) {
+            yk[j] = (j == p) ? 1.0 : zk[j];
+            ek[j] = (j == p) ? 0.0 : 1.0;
+          }
+          __syncwarp();
+          for (int j = lane; j < k; j += 32) g0[j] = gk[j] - ek[j] * gk[p];
+          __syncwarp();
+          // free list in tk (as doubles holding indices) -- built serially by lane 0 (k <= 64)
+          if (lane == 0) {
+            int nf = 0;
+            for (int j = 0; j < k; ++j) {
+              const bool bound = (j == p) || (yk[j] <= 1e-12 && g0[j] > 0.0);
+              if (!bound) { tk[nf++] = (double)j; }
+            }
+            isc[4] = nf;
+          }
+          __syncwarp();
+          nfree = isc[4];
+          for (int a = lane; a < nfree; a += 32) { const double v = g0[(int)tk[a]]; gn = fma(v, v, gn); }
+          gn = Grp<1>::wsum(gn);
+          if (sqrt(gn) < 1e-10) {
+            if (lane == 0) isc[5] = 1;  // converged: return lam
+          } else {
+            // H0 on the free set: H0[a][b] = H[i][j] - H[j][p] - H[i][p] + H[p][p]  (e_i = e_j = 1)
+            for (int a = lane; a < nfree; a += 32) {
+              const int i = (int)tk[a];
+              for (int c2 = 0; c2 < nfree; ++c2) {
+                const int j = (int)tk[c2];
+                Lm[a * ld + c2] = M[i * ld + j] - M[j * ld + p] - M[i * ld + p] + M[p * ld + p];
+              }
+              rk[a] = -g0[i];
+            }
+            __syncwarp();
+            const bool ok = warp_cholesky(Lm, nfree, ld, lane, nullptr);
+            if (!ok) {
+              if (lane == 0) isc[5] = 2;  // solve failure (RL: break; dual: flagged)
+            } else {
+              warp_chol_solve(Lm, nfree, ld, rk, lane);
+              for (int j = lane; j < k; j += 32) dk[j] = 0.0;
+              __syncwarp();
+              double dg = 0.0, dmax = 0.0;
+              for (int a = lane; a < nfree; a += 32) {
+                const int i = (int)tk[a];
+                dk[i] = rk[a];
+                dg = fma(rk[a], g0[i], dg);
+                dmax = fmax(dmax, fabs(rk[a]));
+              }
+              dg = Grp<1>::wsum(dg);
+              dmax = Grp<1>::wmax(dmax);
+              if (lane == 0) {
+                isc[5] = 0;
+                sc[5] = F; sc[6] = dg; sc[7] = dmax;
+                sc[8] = rl ? fmin(1.0 / dmax, 1.0) : 1.0;  // tau
+                isc[6] = p;
+              }
+            }
+          }
+          __syncwarp();
+        }
+        g.sync();
+        if (isc[5] == 1) { inner_its = it; break; }
+        if (isc[5] == 2) { fail = 1; break; }
+        const int p = isc[6];
+        // projected backtracking line search
+        bool ret_now = false;
+        for (int bt = 0; bt < maxback; ++bt) {
+          const double tau = sc[8];
+          if (g.warp == 0) {
+            const int lane = g.lane;
+            double es = 0.0;
+            for (int j = lane; j < k; j += 32) {
+              double yn = fmax(yk[j] + tau * dk[j], 0.0);
+              if (j == p) yn = 1.0;
+              lnk[j] = yn;
+              es = fma(ek[j], yn, es);
+            }
+            es = Grp<1>::wsum(es);
+            __syncwarp();
+            if (lane == 0) lnk[p] = 1.0 - es;
+            __syncwarp();
+          }
+          g.sync();
+          bool accept = false;
+          if (lnk[p] >= 0.0) {
+            if (cf.line_search) {
+              double fs2 = 0.0;
+              for (int e = g.tid; e < n; e += g.T) {
+                double a = 0.0;
+                for (int j = 0; j < k; ++j) a = fma((double)__ldg(rowp[j] + e), lnk[j], a);
+                fs2 += softplus_d(a);
+              }
+              fs2 = g.sum(fs2);
+              double cl = 0.0;
+              for (int j = 0; j < k; ++j) cl = fma(ck[j], lnk[j], cl);
+              const double Fn = fs2 - cl;
+              accept = Fn < sc[5] + tau * 1e-5 * sc[6];
+            } else {
+              accept = true;
+            }
+          }
+          if (accept) break;
+          const bool small = rl ? (tau * sc[7] < 1e-10) : (tau < 1e-10);
+          if (small) { ret_now = true; break; }
+          g.sync();
+          if (g.tid == 0) sc[8] = tau * 0.5;
+          g.sync();
+        }
+        g.sync();
+        for (int j = g.tid; j < k; j += g.T) zk[j] = lnk[j];
+        g.sync();
+        if (ret_now) done = true;
+      }
+    }
+    // y = 1 / (1 + exp(G^T lam))   (:165 / :168)
+    for (int e = g.tid; e < n; e += g.T) {
+      double a = 0.0;
+      for (int j = 0; j < k; ++j) a = fma((double)__ldg(rowp[j] + e), zk[j], a);
+      yv[e] = 1.0 / (1.0 + exp(a));
+    }
+    g.sync();
+  }
+
+  // ---- commit: y, lambda, prune, bookkeeping -------------------------------------------------
+  double maxdiff = 0.0, bad = 0.0;
+  const bool rl = (cf.variant == ICNN_VARIANT_RL);
+  for (int e = g.tid; e < n; e += g.T) {
+    double ye = yv[e];
+    if (rl) ye = fmin(fmax(ye, 0.03), 0.97);  // RL/src/bundle_entropy.py:118,123
+    if (!isfinite(ye)) bad = 1.0;
+    maxdiff = fmax(maxdiff, fabs(yu[e] - ye));
+    yu[e] = ye;
+    b.y32[(size_t)u * n + e] = (float)ye;
+  }
+  if (rl) maxdiff = g.max(maxdiff);
+  bad = g.max(bad);
+  if (g.warp == 0) {
+    const int lane = g.lane;
+    // prune (keep lam > thr), rebuild perm: kept slots, then dropped, then the old free tail
+    if (lane == 0) {
+      int nk = 0;
+      int dropped[64];
+      int nd = 0;
+      int* pw = b.perm + (size_t)u * KS;
+      int oldp[64];
+      for (int j = 0; j < k; ++j) oldp[j] = pw[j];
+      for (int j = 0; j < k; ++j) {
+        const double lj = zk[j];
+        if (lj > cf.prune_thr) { pw[nk++] = oldp[j]; lamu[oldp[j]] = lj; }
+        else dropped[nd++] = oldp[j];
+      }
+      for (int j = 0; j < nd; ++j) pw[nk + j] = dropped[j];
+      b.count[u] = nk;
+      int fin = 0;
+      int stt = ICNN_ST_RUNNING;
+      if (fail) stt = ICNN_ST_SOLVE_FAIL;
+      if (bad > 0.0) { stt = ICNN_ST_NONFINITE; fin = 1; }
+      if (rl && maxdiff < 1e-6) { fin = 1; if (stt == ICNN_ST_RUNNING) stt = ICNN_ST_CONVERGED; }
+      b.status[u] = stt;
+      if (fin) b.finished[u] = 1;
+      else atomicAdd(&b.nactive[A.t + 1], 1);
+      if (b.newton_its) b.newton_its[u] += inner_its;
+    }
+  }
+}
+
+__global__ void bundle_init_kernel(icnn_bundle_bufs b, int nIterMax, int nIterDefault) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long tot = (long long)b.B * b.KS;
+  if (i < tot) b.perm[i] = (int)(i % b.KS);
+  if (i < b.B) {
+    b.count[i] = 0; b.status[i] = 0; b.finished[i] = 0; b.nIters[i] = nIterDefault;
+    if (b.newton_its) b.newton_its[i] = 0;
+  }
+  if (i <= nIterMax) b.nactive[i] = (i == 0) ? b.B : 0;
+}
+
+__global__ void y_round_kernel(const double* y, float* y32, long long N) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < N) y32[i] = (float)y[i];
+}
+
+__global__ void put_fg_kernel(icnn_bundle_bufs b, const float* f, const float* gsrc) {
+  const int u = blockIdx.x;
+  const int slot = b.perm[(size_t)u * b.KS + b.count[u]];
+  float* dst = b.G + ((size_t)u * b.KS + slot) * b.n;
+  for (int e = threadIdx.x; e < b.n; e += blockDim.x) dst[e] = gsrc[(size_t)u * b.n + e];
+  if (threadIdx.x == 0) b.f[u] = f[u];
+}
+
+static int pick_wps(int n) { return n <= 128 ? 1 : 8; }
+
+int bundle_step_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int t, cudaStream_t st) {
+  StepArgs a;
+  a.b = *b; a.c = *cfg; a.t = t;
+  a.npad = (b->n + 3) & ~3;
+  a.ld = b->KS | 1;
+  const int wps = pick_wps(b->n);
+  const size_t smem = sizeof(double) * group_smem_doubles(a.npad, b->KS, a.ld, wps) * (8 / wps);
+  if (smem > 227 * 1024) {
+    set_error("bundle_step: shared memory %zu B exceeds 227 KB (n=%d, KS=%d)", smem, b->n, b->KS);
+    return ICNN_E_UNSUPPORTED;
+  }
+  if (b->KS > 64) { set_error("bundle_step: KS=%d > 64 unsupported", b->KS); return ICNN_E_UNSUPPORTED; }
+  cudaError_t e;
+  if (wps == 1) {
+    e = cudaFuncSetAttribute(bundle_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
+    bundle_step_kernel<1><<<cdiv(b->B, 8), 256, smem, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(bundle_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
+    bundle_step_kernel<8><<<b->B, 256, smem, st>>>(a);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("bundle_step launch: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
+  return ICNN_OK;
+}
+
+}  // namespace icnn
+
+using namespace icnn;
+
+static int check_bufs(const icnn_bundle_bufs* b) {
+  ICNN_REQUIRE(b, "null bufs");
+  ICNN_REQUIRE(b->B > 0 && b->n > 0 && b->KS >= 2, "bad B / n / KS");
+  ICNN_REQUIRE(b->y && b->y32 && b->f && b->G && b->h && b->lam && b->rsum && b->gram && b->perm &&
+                   b->count && b->status && b->finished && b->nIters && b->nactive,
+               "null buffer in icnn_bundle_bufs");
+  return ICNN_OK;
+}
+
+extern "C" int icnn_bundle_init(const icnn_bundle_bufs* b, int32_t nIterMax, void* stream) {
+  int rc = check_bufs(b);
+  if (rc) return rc;
+  ICNN_REQUIRE(nIterMax >= 1, "nIterMax < 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long tot = (long long)b->B * b->KS;
+  if (tot < nIterMax + 1) tot = nIterMax + 1;
+  bundle_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(*b, nIterMax, nIterMax);
+  const long long N = (long long)b->B * b->n;
+  y_round_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(b->y, b->y32, N);
+  ICNN_CUDA_CHECK(cudaGetLastError());
+  return ICNN_OK;
+}
+
+extern "C" int icnn_bundle_put_fg(const icnn_bundle_bufs* b, const float* f, const float* g, void* stream) {
+  int rc = check_bufs(b);
+  if (rc) return rc;
+  ICNN_REQUIRE(f && g, "null f/g");
+  put_fg_kernel<<<b->B, 128, 0, static_cast<cudaStream_t>(stream)>>>(*b, f, g);
+  ICNN_CUDA_CHECK(cudaGetLastError());
+  return ICNN_OK;
+}
+
+extern "C" int icnn_bundle_step(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int32_t t, void* stream) {
+  int rc = check_bufs(b);
+  if (rc) return rc;
+  ICNN_REQUIRE(cfg, "null cfg");
+  ICNN_REQUIRE(cfg->variant >= 0 && cfg->variant <= 2, "bad variant");
+  ICNN_REQUIRE(cfg->solver == ICNN_SOLVER_PC || cfg->solver == ICNN_SOLVER_NEWTON, "bad solver");
+  ICNN_REQUIRE(cfg->variant == ICNN_VARIANT_LIB || cfg->solver == ICNN_SOLVER_NEWTON,
+               "dual / rl variants use the Newton solver");
+  ICNN_REQUIRE(t >= 0, "t < 0");
+  return bundle_step_launch(cfg, b, t, static_cast<cudaStream_t>(stream));
+}

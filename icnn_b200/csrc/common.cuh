@@ -1,0 +1,47 @@
+// Shared helpers for libicnn_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/icnn_b200.h"
+
+#define ICNN_MAX_LAYERS 8
+
+namespace icnn {
+
+void set_error(const char* fmt, ...);
+
+#define ICNN_CUDA_CHECK(expr)                                                        \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      icnn::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return ICNN_E_CUDA;                                                            \
+    }                                                                                \
+  } while (0)
+
+#define ICNN_REQUIRE(cond, msg)                                        \
+  do {                                                                 \
+    if (!(cond)) {                                                     \
+      icnn::set_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, msg); \
+      return ICNN_E_INVALID;                                           \
+    }                                                                  \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace icnn
+
+// Library-owned weight descriptor.
+struct icnn_picnn {
+  int n, L;
+  int hidden[ICNN_MAX_LAYERS];
+  float alpha;
+  // Wcat[i], i = 0..L : [(s_{i-1} + n), s_i] row-major = [Wz_i ; Wy_i]  (s_{-1} = 0, s_L = 1)
+  float* Wcat[ICNN_MAX_LAYERS + 1];
+  int width(int i) const { return i < L ? hidden[i] : 1; }
+  int prev(int i) const { return i == 0 ? 0 : hidden[i - 1]; }
+};

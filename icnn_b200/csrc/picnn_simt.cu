@@ -1,0 +1,349 @@
+// K1 (baseline): fully-connected PICNN energy f and df/dy for a whole minibatch, FP32 FFMA.
+//
+// Restates on the GPU what the reference evaluates through TensorFlow:
+//   forward   multi-label-cls/icnn_ebundle.py:349-387, RL/src/icnn.py:356-404
+//   gradient  tf.gradients(E_, y_)  (multi-label-cls/icnn_ebundle.py:146)
+//
+//   a_i = (z_{i-1} o cz_i) Wz_i + (y o cy_i) Wy_i + d_i ,  z_i = act(a_i) (i < L),  f = a_L
+//   delta_L = 1 ;  g += cy_i o (delta_i Wy_i^T) ;  delta_{i-1} = act'(a_{i-1}) o cz_i o (delta_i Wz_i^T)
+//
+// Each hidden layer is one gated GEMM against Wcat_i = [Wz_i ; Wy_i] (forward: K-concatenated,
+// backward: the same buffer read transposed), with the per-sample gates applied while the A tile
+// is staged and bias/activation/act'-mask/g-accumulate fused into the epilogue.  The width-1
+// output layer and its backward seed are a warp-per-sample kernel (shuffle reduction).
+// This FP32 kernel is the accuracy anchor for the tcgen05 path (picnn_tc.cu).
+#include "common.cuh"
+
+namespace icnn {
+
+struct GemmArgs {
+  int M, N, K0, K1;
+  const float* A0; const float* G0; int lda0;
+  const float* A1; const float* G1; int lda1;
+  float a1_scale, a1_shift;
+  const float* W; int ldw;
+  // forward epilogue
+  const float* D; float* Z; float alpha;
+  // backward epilogue
+  int N0; const float* Zprev; const float* Cz; float* dprev;
+  const float* Cy; float* g; long long g_row_stride; const int* perm; const int* count; int KS; int n;
+  float g_scale;
+  const int* skip_if_zero;
+};
+
+constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
+
+__device__ __forceinline__ float* g_row_ptr(const GemmArgs& a, int m) {
+  if (a.perm == nullptr) return a.g + (long long)m * a.g_row_stride;
+  int slot = a.perm[(long long)m * a.KS + a.count[m]];
+  return a.g + ((long long)m * a.KS + slot) * a.n;
+}
+
+// MODE 0: forward (W is [K, N]);  MODE 1: backward (W is [N, K], K = K0, no second segment)
+template <int MODE>
+__global__ void __launch_bounds__(256) gated_gemm_kernel(GemmArgs a) {
+  if (a.skip_if_zero != nullptr && *a.skip_if_zero == 0) return;
+  __shared__ float As[2][BK][BM + PAD];
+  __shared__ float Bs[2][BK][BN + PAD];
+  const int t = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int K = a.K0 + a.K1;
+  const int ty = t / 16, tx = t % 16;
+
+  // loader coordinates
+  const int a_row = t / 4, a_k = (t % 4) * 4;  // A tile: 64 rows x 16 k
+  const int b_k = t / 16, b_n = (t % 16) * 4;  // fwd W tile: 16 k x 64 n
+  const int bt_n = t / 4, bt_k = (t % 4) * 4;  // bwd W tile: 64 n x 16 k
+
+  float ra[4], rb[4];
+  auto load_tiles = [&](int k0) {
+    const int m = m0 + a_row;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = k0 + a_k + i;
+      float v = 0.f;
+      if (m < a.M && kk < K) {
+        if (kk < a.K0) {
+          v = a.A0[(long long)m * a.lda0 + kk];
+          if (a.G0) v *= a.G0[(long long)m * a.lda0 + kk];
+        } else {
+          const int k1 = kk - a.K0;
+          v = fmaf(a.a1_scale, a.A1[(long long)m * a.lda1 + k1], a.a1_shift);
+          if (a.G1) v *= a.G1[(long long)m * a.lda1 + k1];
+        }
+      }
+      ra[i] = v;
+    }
+    if (MODE == 0) {
+      const int kk = k0 + b_k;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int nn = n0 + b_n + i;
+        rb[i] = (kk < K && nn < a.N) ? a.W[(long long)kk * a.ldw + nn] : 0.f;
+      }
+    } else {
+      const int nn = n0 + bt_n;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = k0 + bt_k + i;
+        rb[i] = (kk < K && nn < a.N) ? a.W[(long long)nn * a.ldw + kk] : 0.f;
+      }
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) As[buf][a_k + i][a_row] = ra[i];
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[buf][b_k][b_n + i] = rb[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[buf][bt_k + i][bt_n] = rb[i];
+    }
+  };
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int nk = (K + BK - 1) / BK;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w};
+      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) store_tiles(buf ^ 1);
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= a.M) continue;
+    float* grow = (MODE == 1) ? g_row_ptr(a, m) : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nn = n0 + tx * 4 + j;
+      if (nn >= a.N) continue;
+      if (MODE == 0) {
+        const float v = acc[i][j] + a.D[(long long)m * a.N + nn];
+        a.Z[(long long)m * a.N + nn] = v > 0.f ? v : a.alpha * v;
+      } else {
+        if (nn < a.N0) {
+          const long long idx = (long long)m * a.N0 + nn;
+          const float da = a.Zprev[idx] > 0.f ? 1.f : a.alpha;
+          a.dprev[idx] = da * a.Cz[idx] * acc[i][j];
+        } else {
+          const int e = nn - a.N0;
+          grow[e] = fmaf(a.g_scale * a.Cy[(long long)m * a.n + e], acc[i][j], grow[e]);
+        }
+      }
+    }
+  }
+}
+
+struct OutArgs {
+  int M, S, n;                  // S = s_{L-1}
+  const float* Z; const float* Cz;      // [M, S]
+  const float* y; const float* Cy;      // [M, n]
+  const float* D;                        // [M]
+  const float* w;                        // [S + n]  = [wz_L ; wy_L]
+  float in_scale, in_shift, g_scale, alpha;
+  float* f; float* delta;                // [M], [M, S]
+  float* g; long long g_row_stride; const int* perm; const int* count; int KS;
+  const int* skip_if_zero;
+};
+
+// warp per sample: f = d_L + (z o cz_L).wz_L + (y o cy_L).wy_L ; seeds delta_{L-1} and g.
+__global__ void __launch_bounds__(256) out_layer_kernel(OutArgs a) {
+  if (a.skip_if_zero != nullptr && *a.skip_if_zero == 0) return;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= a.M) return;
+  const int m = warp;
+  float acc = 0.f;
+  for (int j = lane; j < a.S; j += 32) {
+    const long long idx = (long long)m * a.S + j;
+    const float z = a.Z[idx], c = a.Cz[idx] * a.w[j];
+    acc = fmaf(z, c, acc);
+    a.delta[idx] = (z > 0.f ? 1.f : a.alpha) * c;
+  }
+  float* grow;
+  if (a.perm == nullptr) grow = a.g + (long long)m * a.g_row_stride;
+  else grow = a.g + ((long long)m * a.KS + a.perm[(long long)m * a.KS + a.count[m]]) * a.n;
+  for (int e = lane; e < a.n; e += 32) {
+    const long long idx = (long long)m * a.n + e;
+    const float c = a.Cy[idx] * a.w[a.S + e];
+    acc = fmaf(fmaf(a.in_scale, a.y[idx], a.in_shift), c, acc);
+    grow[e] = a.g_scale * c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) a.f[m] = acc + a.D[m];
+}
+
+__global__ void concat_rows_kernel(float* dst, const float* top, long long ntop, const float* bot,
+                                   long long nbot) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < ntop) dst[i] = top[i];
+  else if (i < ntop + nbot) dst[i] = bot[i - ntop];
+}
+
+// momentum GD update, multi-label-cls/icnn-back.py:122-128
+__global__ void gd_update_kernel(float* y, float* v, const float* g, long long N, float lr, float mom) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float vp = v[i];
+  const float vn = mom * vp - lr * g[i];
+  y[i] = y[i] - mom * vp + (1.f + mom) * vn;
+  v[i] = vn;
+}
+
+// workspace layout: Z_0..Z_{L-1} [B, s_i], then two delta buffers [B, smax]
+static size_t ws_floats(const icnn_picnn* h, int B, size_t* zoff, size_t* doff) {
+  size_t off = 0;
+  int smax = 0;
+  for (int i = 0; i < h->L; ++i) {
+    if (zoff) zoff[i] = off;
+    off += (size_t)B * h->hidden[i];
+    off = (off + 63) & ~(size_t)63;
+    smax = h->hidden[i] > smax ? h->hidden[i] : smax;
+  }
+  if (doff) { doff[0] = off; doff[1] = off + (((size_t)B * smax + 63) & ~(size_t)63); }
+  off += 2 * (((size_t)B * smax + 63) & ~(size_t)63);
+  return off;
+}
+
+int picnn_fg_simt(const icnn_picnn* h, const icnn_gates* gt, const float* y32, float* f, float* g,
+                  long long g_row_stride, const int* perm, const int* count, int KS, void* workspace,
+                  const int* skip, cudaStream_t st) {
+  const int B = gt->B, n = h->n, L = h->L;
+  size_t zoff[ICNN_MAX_LAYERS], doff[2];
+  ws_floats(h, B, zoff, doff);
+  float* ws = static_cast<float*>(workspace);
+  float* Z[ICNN_MAX_LAYERS];
+  for (int i = 0; i < L; ++i) Z[i] = ws + zoff[i];
+  float* dl[2] = {ws + doff[0], ws + doff[1]};
+
+  for (int i = 0; i < L; ++i) {  // forward hidden layers
+    GemmArgs a{};
+    a.M = B; a.N = h->hidden[i]; a.K0 = h->prev(i); a.K1 = n;
+    a.A0 = i ? Z[i - 1] : nullptr; a.G0 = i ? gt->cz[i] : nullptr; a.lda0 = a.K0;
+    a.A1 = y32; a.G1 = gt->cy[i]; a.lda1 = n; a.a1_scale = gt->in_scale; a.a1_shift = gt->in_shift;
+    a.W = h->Wcat[i]; a.ldw = a.N;
+    a.D = gt->d[i]; a.Z = Z[i]; a.alpha = h->alpha; a.skip_if_zero = skip;
+    dim3 grid(cdiv(a.N, BN), cdiv(B, BM));
+    gated_gemm_kernel<0><<<grid, 256, 0, st>>>(a);
+  }
+  {
+    OutArgs o{};
+    o.M = B; o.S = h->hidden[L - 1]; o.n = n; o.Z = Z[L - 1]; o.Cz = gt->cz[L]; o.y = y32; o.Cy = gt->cy[L];
+    o.D = gt->d[L]; o.w = h->Wcat[L]; o.in_scale = gt->in_scale; o.in_shift = gt->in_shift;
+    o.g_scale = gt->g_scale; o.alpha = h->alpha; o.f = f; o.delta = dl[0];
+    o.g = g; o.g_row_stride = g_row_stride; o.perm = perm; o.count = count; o.KS = KS; o.skip_if_zero = skip;
+    out_layer_kernel<<<cdiv(B * 32, 256), 256, 0, st>>>(o);
+  }
+  int cur = 0;
+  for (int i = L - 1; i >= 0; --i) {  // backward hidden layers
+    GemmArgs a{};
+    a.M = B; a.N0 = h->prev(i); a.N = a.N0 + n; a.K0 = h->hidden[i]; a.K1 = 0;
+    a.A0 = dl[cur]; a.G0 = nullptr; a.lda0 = a.K0;
+    a.W = h->Wcat[i]; a.ldw = a.K0; a.alpha = h->alpha;
+    a.Zprev = i ? Z[i - 1] : nullptr; a.Cz = i ? gt->cz[i] : nullptr; a.dprev = dl[cur ^ 1];
+    a.Cy = gt->cy[i]; a.g = g; a.g_row_stride = g_row_stride; a.perm = perm; a.count = count; a.KS = KS;
+    a.n = n; a.g_scale = gt->g_scale; a.skip_if_zero = skip;
+    dim3 grid(cdiv(a.N, BN), cdiv(B, BM));
+    gated_gemm_kernel<1><<<grid, 256, 0, st>>>(a);
+    cur ^= 1;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("picnn_fg launch: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
+  return ICNN_OK;
+}
+
+}  // namespace icnn
+
+using namespace icnn;
+
+extern "C" int icnn_picnn_create(const icnn_picnn_desc* d, icnn_picnn_t** out, void* stream) {
+  ICNN_REQUIRE(d && out, "null descriptor");
+  ICNN_REQUIRE(d->L >= 1 && d->L <= ICNN_MAX_LAYERS, "L must be in [1, 8]");
+  ICNN_REQUIRE(d->n >= 1, "n must be positive");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  icnn_picnn* h = new icnn_picnn();
+  h->n = d->n; h->L = d->L; h->alpha = d->alpha;
+  for (int i = 0; i < d->L; ++i) {
+    if (d->hidden[i] < 1) { delete h; set_error("hidden width must be positive"); return ICNN_E_INVALID; }
+    h->hidden[i] = d->hidden[i];
+  }
+  for (int i = 0; i <= d->L; ++i) h->Wcat[i] = nullptr;
+  for (int i = 0; i <= d->L; ++i) {
+    const long long si = h->width(i), sp = h->prev(i);
+    const long long ntop = sp * si, nbot = (long long)h->n * si;
+    if (!d->Wy[i] || (i > 0 && !d->Wz[i])) { icnn_picnn_destroy(h); set_error("null weight pointer, layer %d", i); return ICNN_E_INVALID; }
+    cudaError_t e = cudaMalloc(&h->Wcat[i], sizeof(float) * (ntop + nbot));
+    if (e != cudaSuccess) { icnn_picnn_destroy(h); set_error("cudaMalloc weights: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
+    const long long tot = ntop + nbot;
+    concat_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->Wcat[i], d->Wz[i], ntop, d->Wy[i], nbot);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { icnn_picnn_destroy(h); set_error("picnn_create: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
+  *out = h;
+  return ICNN_OK;
+}
+
+extern "C" int icnn_picnn_destroy(icnn_picnn_t* h) {
+  if (!h) return ICNN_OK;
+  for (int i = 0; i <= h->L && i <= ICNN_MAX_LAYERS; ++i)
+    if (h->Wcat[i]) cudaFree(h->Wcat[i]);
+  delete h;
+  return ICNN_OK;
+}
+
+extern "C" size_t icnn_picnn_workspace_bytes(const icnn_picnn_t* h, int32_t B) {
+  if (!h || B <= 0) return 0;
+  return sizeof(float) * ws_floats(h, B, nullptr, nullptr);
+}
+
+extern "C" int icnn_picnn_fg(const icnn_picnn_t* h, const icnn_gates* gates, const float* y32, float* f,
+                             float* g, int64_t g_row_stride, const int32_t* perm, const int32_t* count,
+                             int32_t KS, void* workspace, const int32_t* skip_if_zero, void* stream) {
+  ICNN_REQUIRE(h && gates && y32 && f && g && workspace, "null pointer");
+  ICNN_REQUIRE(gates->B > 0, "empty batch");
+  ICNN_REQUIRE((perm == nullptr) == (count == nullptr), "perm and count go together");
+  return picnn_fg_simt(h, gates, y32, f, g, g_row_stride, perm, count, KS, workspace, skip_if_zero,
+                       static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int icnn_gd_solve(const icnn_picnn_t* h, const icnn_gates* gates, float* y32, float* v, float* g,
+                             float* f_out, int32_t nIter, float lr, float momentum, void* workspace,
+                             void* stream) {
+  ICNN_REQUIRE(h && gates && y32 && v && g && f_out && workspace, "null pointer");
+  ICNN_REQUIRE(nIter >= 0, "nIter < 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long N = (long long)gates->B * h->n;
+  ICNN_CUDA_CHECK(cudaMemsetAsync(v, 0, sizeof(float) * N, st));
+  for (int it = 0; it < nIter; ++it) {
+    int rc = picnn_fg_simt(h, gates, y32, f_out, g, h->n, nullptr, nullptr, 0, workspace, nullptr, st);
+    if (rc) return rc;
+    gd_update_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(y32, v, g, N, lr, momentum);
+  }
+  int rc = picnn_fg_simt(h, gates, y32, f_out, g, h->n, nullptr, nullptr, 0, workspace, nullptr, st);
+  if (rc) return rc;
+  ICNN_CUDA_CHECK(cudaGetLastError());
+  return ICNN_OK;
+}
