@@ -47,7 +47,7 @@ class BundleBufs(C.Structure):
                 ("ys", C.c_void_p), ("h", C.c_void_p), ("lam", C.c_void_p), ("rsum", C.c_void_p),
                 ("gram", C.c_void_p), ("perm", C.c_void_p), ("count", C.c_void_p),
                 ("status", C.c_void_p), ("finished", C.c_void_p), ("nIters", C.c_void_p),
-                ("nactive", C.c_void_p), ("newton_its", C.c_void_p)]
+                ("nactive", C.c_void_p), ("newton_its", C.c_void_p), ("ksum", C.c_void_p)]
 
 
 class BundleCfg(C.Structure):

@@ -88,11 +88,12 @@ class BundleState:
         self.nIters = e(B, dtype=i32)
         self.nactive = e(nIter + 1, dtype=i32)
         self.newton_its = e(B, dtype=i32)
+        self.ksum = e(B, dtype=i32)
         p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         self.c = _capi.BundleBufs(self.B, self.n, self.KS, p(self.y), p(self.y32), p(self.f), p(self.G),
                                   p(self.ys), p(self.h), p(self.lam), p(self.rsum), p(self.gram),
                                   p(self.perm), p(self.count), p(self.status), p(self.finished),
-                                  p(self.nIters), p(self.nactive), p(self.newton_its))
+                                  p(self.nIters), p(self.nactive), p(self.newton_its), p(self.ksum))
         self._host = None
 
     # ---- ragged outputs ---------------------------------------------------------------------

@@ -755,6 +755,7 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
       if (fin) b.finished[u] = 1;
       else atomicAdd(&b.nactive[A.t + 1], 1);
       if (b.newton_its) b.newton_its[u] += inner_its;
+      if (b.ksum) b.ksum[u] += k;
     }
   }
 }
@@ -766,6 +767,7 @@ __global__ void bundle_init_kernel(icnn_bundle_bufs b, int nIterMax, int nIterDe
   if (i < b.B) {
     b.count[i] = 0; b.status[i] = 0; b.finished[i] = 0; b.nIters[i] = nIterDefault;
     if (b.newton_its) b.newton_its[i] = 0;
+    if (b.ksum) b.ksum[i] = 0;
   }
   if (i <= nIterMax) b.nactive[i] = (i == 0) ? b.B : 0;
 }

@@ -1,0 +1,59 @@
+"""Sample-sharded multi-GPU inner loop: one process per GPU, no data-path collective except a
+single all-gather of the solved y* at the end.
+
+Every sample's bundle, dual solve and iterate are independent (the reference loops
+``for u in range(bsize)``, lib/bundle_entropy.py:211), so rows are split into contiguous blocks,
+theta is replicated, and the only exchange is the final gather.  ``torch.distributed`` (NCCL on
+GPUs, gloo in the CPU tests) is the plumbing.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_rows(B, rank, world_size):
+    """Contiguous row block [lo, hi) of rank ``rank``; the first B % ws ranks get one extra row."""
+    base, rem = divmod(int(B), int(world_size))
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def shard_sizes(B, world_size):
+    return [shard_rows(B, r, world_size)[1] - shard_rows(B, r, world_size)[0] for r in range(world_size)]
+
+
+def allgather_rows(y_local, B, group=None):
+    """All-gather row blocks [b_r, n] -> [B, n] on every rank (ragged last blocks allowed).
+    Every rank must call it, including ranks whose samples all finished early."""
+    ws = dist.get_world_size(group)
+    sizes = shard_sizes(B, ws)
+    n = y_local.shape[1]
+    if len(set(sizes)) == 1:
+        out = torch.empty(B, n, dtype=y_local.dtype, device=y_local.device)
+        dist.all_gather_into_tensor(out, y_local.contiguous(), group=group)
+        return out
+    mx = max(sizes)
+    pad = torch.zeros(mx, n, dtype=y_local.dtype, device=y_local.device)
+    pad[: y_local.shape[0]] = y_local
+    parts = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+
+
+def solve_batch_sharded(net, x, y0, nIter=None, solver="pc", variant="lib", affine=False, group=None,
+                        **kw):
+    """Rank-local fused solveBatch on this rank's row block of (x, y0), then one all-gather of
+    y*.  ``net`` is this rank's PICNN replica.  Returns (y_all [B, n] float64 CUDA tensor,
+    local result tuple)."""
+    from . import bundle_entropy
+    rank, ws = dist.get_rank(group), dist.get_world_size(group)
+    B = x.shape[0]
+    lo, hi = shard_rows(B, rank, ws)
+    fg = net.bind(x[lo:hi], affine=affine)
+    out = bundle_entropy.solveBatch(fg, y0[lo:hi].copy(), nIter=nIter, solver=solver, variant=variant,
+                                    return_state=True, **kw)
+    st = out[-1]
+    y_all = allgather_rows(st.y, B, group=group)
+    return y_all, out[:-1]

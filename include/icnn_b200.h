@@ -96,6 +96,8 @@ typedef struct {
   int32_t* nIters;   /* [B]  the reference's nIters list                               */
   int32_t* nactive;  /* [nIterMax+1] unfinished samples entering iteration t           */
   int32_t* newton_its; /* [B] accumulated inner (IPM / Newton) iterations, diagnostics */
+  int32_t* ksum;     /* [B] sum over executed iterations of the active row count k_t
+                        (algorithmic-bytes accounting for the roofline) */
 } icnn_bundle_bufs;
 
 typedef struct {

@@ -22,68 +22,7 @@ from __future__ import annotations
 import numpy as np
 
 
-class PicnnParams:
-    """Weights of a fully-connected PICNN.
-
-    hidden : list of z-layer widths s_0..s_{L-1} (the output layer of width 1 is implicit).
-    Wy[i]  : [n, s_i]         'z{i}_yu/W'       (bias-free, unconstrained)
-    Wz[i]  : [s_{i-1}, s_i]   'z{i}_zu_proj/W'  (bias-free, >= 0), i >= 1 (Wz[0] is None)
-    x-path (evaluated once per solveBatch, outside the hot loop):
-      Wu[i], bu[i]   : u_i = u_{i-1} @ Wu[i] + bu[i]  (relu for i < L-1), i = 0..L-1
-      Wzu[i], bzu[i] : cz_i = relu(P_i @ Wzu[i] + bzu[i])   in R^{s_{i-1}}, i >= 1
-      Wyu[i], byu[i] : cy_i =      P_i @ Wyu[i] + byu[i]    in R^{n}
-      Wzx[i], bzx[i] : d_i  =      P_i @ Wzx[i] + bzx[i]    in R^{s_i}
-      with P_0 = x, P_i = u_{i-1}.
-    alpha : leaky-ReLU slope on the z path (0 -> ReLU, multi-label; 0.01 RL).
-    """
-
-    def __init__(self, m, n, hidden, alpha=0.0):
-        self.m, self.n, self.hidden, self.alpha = int(m), int(n), [int(s) for s in hidden], float(alpha)
-        self.L = len(self.hidden)
-        self.sizes = self.hidden + [1]
-        L = self.L
-        self.Wy = [None] * (L + 1)
-        self.Wz = [None] * (L + 1)
-        self.Wu, self.bu = [None] * L, [None] * L
-        self.Wzu, self.bzu = [None] * (L + 1), [None] * (L + 1)
-        self.Wyu, self.byu = [None] * (L + 1), [None] * (L + 1)
-        self.Wzx, self.bzx = [None] * (L + 1), [None] * (L + 1)
-
-    def prev_width(self, i):
-        """Width of P_i (the x-path activation feeding layer i's gates)."""
-        return self.m if i == 0 else self.hidden[i - 1]
-
-
-def synth_params(seed, m, n, hidden, alpha=0.0, gate_bias=0.0, dtype=np.float32):
-    """Seeded synthetic weights: Wy ~ N(0,1/n), Wz = |N(0,1/s_prev)|,
-    x-path/gate weights N(0, 1/fan_in), biases 0 (RL: gate biases 1, RL/src/icnn.py:364,375).
-    Values are rounded to ``dtype`` (float32 = what the device stores) but returned as float64
-    arrays so oracle and device see bit-identical parameters."""
-    rs = np.random.RandomState(seed)
-    p = PicnnParams(m, n, hidden, alpha)
-    L = p.L
-
-    def rnd(shape, fan_in):
-        return (rs.randn(*shape) / np.sqrt(fan_in)).astype(dtype).astype(np.float64)
-
-    for i in range(L):
-        fin = p.prev_width(i)
-        p.Wu[i] = rnd((fin, p.hidden[i]), fin)
-        p.bu[i] = np.zeros(p.hidden[i])
-    for i in range(L + 1):
-        fin = p.prev_width(i)
-        si = p.sizes[i]
-        if i > 0:
-            sp = p.sizes[i - 1]
-            p.Wzu[i] = rnd((fin, sp), fin)
-            p.bzu[i] = np.full(sp, gate_bias)
-            p.Wz[i] = np.abs(rnd((sp, si), sp))
-        p.Wyu[i] = rnd((fin, n), fin)
-        p.byu[i] = np.full(n, gate_bias)
-        p.Wy[i] = rnd((n, si), n)
-        p.Wzx[i] = rnd((fin, si), fin)
-        p.bzx[i] = np.zeros(si)
-    return p
+from icnn_b200.workloads import PicnnParams, synth_params  # noqa: E402,F401  (data generator only)
 
 
 def gates(p: PicnnParams, x):

@@ -1,68 +1,3 @@
-"""Seeded synthetic workloads (SURVEY.md section 8d / BASELINE.md section 4).
-
-TEST INFRASTRUCTURE ONLY.  Data files of the reference are not in the repo and there is no
-network, so every configuration is synthetic at the reference's dimensions.  Everything is
-generated from ``np.random.RandomState(seed)``; float32-representable values returned as
-float64 so the oracle and the device see bit-identical inputs.
-"""
-from __future__ import annotations
-
-import numpy as np
-
-from . import picnn_np
-
-# name -> dict(m, n, hidden, B, nIter, variant, alpha, gate_bias, affine, seed, y0)
-CONFIGS = {
-    # configs[0]: plumbing, the reference's CPU-runnable case
-    "C1": dict(m=8, n=8, hidden=[16, 16], B=64, nIter=5, variant="lib", alpha=0.0, gate_bias=0.0,
-               affine=False, seed=1, y0="half", xdist="normal"),
-    # configs[1]: Olivetti dims, FC stand-in for the conv PICNN (completion/icnn_ebundle.py:345)
-    "C2": dict(m=2048, n=2048, hidden=[512, 512], B=400, nIter=30, variant="lib", alpha=0.0,
-               gate_bias=0.0, affine=False, seed=2, y0="meanvec", xdist="normal"),
-    # configs[2]: Bibtex dims, layerSizes [600] -> [600, 159] (multi-label-cls/icnn_ebundle.py:321-323)
-    "C3": dict(m=1836, n=159, hidden=[600, 159], B=4096, nIter=10, variant="lib", alpha=0.0,
-               gate_bias=0.0, affine=False, seed=3, y0="half", xdist="normal"),
-    # configs[3]: RL HalfCheetah dims (RL/src/agent.py: l1size=l2size=200, lrelu=0.01)
-    "C4": dict(m=17, n=6, hidden=[200, 200], B=65536, nIter=5, variant="rl", alpha=0.01,
-               gate_bias=1.0, affine=True, seed=4, y0="half", xdist="uniform"),
-    # configs[4]: stress
-    "C5": dict(m=512, n=4096, hidden=[1024, 1024, 1024, 1024], B=8192, nIter=50, variant="lib",
-               alpha=0.0, gate_bias=0.0, affine=False, seed=5, y0="half", xdist="normal"),
-    # north_star target shape (batch 4096 / n_y 512)
-    "T": dict(m=512, n=512, hidden=[1024, 1024], B=4096, nIter=10, variant="lib", alpha=0.0,
-              gate_bias=0.0, affine=False, seed=6, y0="half", xdist="normal"),
-}
-
-
-WY_SCALE = {"C1": 3.0, "C2": 3.0, "C3": 3.0, "C4": 1.0, "C5": 3.0, "T": 3.0}
-for _k, _v in WY_SCALE.items():
-    # W^y ~ N(0, wy_scale^2 / n).  SURVEY.md section 8d proposes N(0, 1/n); measured here, that makes
-    # the ReLU PICNN so flat that every sample hits the duplicate-row stop after ~5 iterations
-    # (C2: all 30-iteration solves end at t=5 with k<=6).  Scale 3 gives the bundle growth the
-    # survey describes (C2: k up to 25, mean 17 iterations) -- see DESIGN.md "workloads".
-    CONFIGS[_k]["wy_scale"] = _v
-
-
-def make_inputs(cfg, B=None, seed=None):
-    """Returns (params, x [B,m] float64, y0 [B,n] float64) for a config dict (or name)."""
-    if isinstance(cfg, str):
-        cfg = CONFIGS[cfg]
-    B = cfg["B"] if B is None else B
-    seed = cfg["seed"] if seed is None else seed
-    p = picnn_np.synth_params(seed, cfg["m"], cfg["n"], cfg["hidden"], alpha=cfg["alpha"],
-                              gate_bias=cfg["gate_bias"])
-    sc = np.float32(cfg.get("wy_scale", 1.0))
-    for i in range(len(p.Wy)):
-        p.Wy[i] = (p.Wy[i].astype(np.float32) * sc).astype(np.float64)
-    rs = np.random.RandomState(seed + 1000)
-    if cfg["xdist"] == "uniform":
-        x = rs.uniform(-1.0, 1.0, size=(B, cfg["m"]))
-    else:
-        x = rs.randn(B, cfg["m"])
-    x = x.astype(np.float32).astype(np.float64)
-    if cfg["y0"] == "meanvec":   # completion/icnn_ebundle.py:223 starts from the per-pixel mean
-        v = rs.uniform(0.2, 0.8, size=(1, cfg["n"])).astype(np.float32).astype(np.float64)
-        y0 = np.repeat(v, B, axis=0)
-    else:
-        y0 = np.full((B, cfg["n"]), 0.5)
-    return p, x, y0
+"""Seeded synthetic workloads -- re-exported from icnn_b200/workloads.py (a pure-numpy data
+generator shared with bench.py; it contains no algorithm).  TEST INFRASTRUCTURE ONLY."""
+from icnn_b200.workloads import CONFIGS, WY_SCALE, make_inputs  # noqa: F401

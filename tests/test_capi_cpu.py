@@ -1,0 +1,75 @@
+"""CPU-only checks of the boundary: the shared library loads, exports every symbol the header
+declares, rejects bad arguments, and fails loudly (no CPU fallback) without a device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from icnn_b200 import _capi
+    hdr = open(os.path.join(ROOT, "include", "icnn_b200.h")).read()
+    declared = set(re.findall(r"\b(icnn_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_capi.SYMBOLS), declared ^ set(_capi.SYMBOLS)
+    lib = C.CDLL(_capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _capi.lib.icnn_abi_version() == _capi.ABI_VERSION
+
+
+def test_struct_layouts_match_header_sizes():
+    from icnn_b200 import _capi
+    # 3 int32 (+pad) + 17 pointers ; cfg: 4 int32 + 2 double + 2 int32
+    assert C.sizeof(_capi.BundleBufs) == 16 + 17 * 8
+    assert C.sizeof(_capi.BundleCfg) == 16 + 16 + 8
+    assert C.sizeof(_capi.Gates) == 8 + 3 * 8 + 12 + 4
+    assert C.sizeof(_capi.PicnnDesc) == 8 + 8 + 8 + 8 + 8
+
+
+def test_bad_arguments_are_rejected_without_touching_the_gpu():
+    from icnn_b200 import _capi
+    rc = _capi.lib.icnn_picnn_create(None, None, None)
+    assert rc == -1 and b"null" in _capi.lib.icnn_last_error()
+    bufs = _capi.BundleBufs()
+    assert _capi.lib.icnn_bundle_init(C.byref(bufs), 5, None) == -1
+    cfg = _capi.BundleCfg()
+    assert _capi.lib.icnn_bundle_step(C.byref(cfg), C.byref(bufs), 0, None) == -1
+    with pytest.raises(_capi.IcnnError):
+        _capi.check(-1)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    import icnn_b200
+    from icnn_b200 import bundle_entropy, workloads
+    p, x, y0 = workloads.make_inputs("C1", B=4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        icnn_b200.PICNN.from_params(p)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        bundle_entropy.solveBatch(lambda y: (np.zeros(4), np.zeros_like(y)), y0)
+
+
+def test_unknown_solver_raises_like_reference():
+    # lib/bundle_entropy.py:232  raise RuntimeError("Solver unknown: "+solver)
+    from icnn_b200 import bundle_entropy
+    with pytest.raises(RuntimeError, match="Solver unknown"):
+        bundle_entropy._make_cfg("lib", "simplex", 10, None, None, 0, 8, 9)
+    assert bundle_entropy._make_cfg("lib", "boyd", 10, None, None, 0, 8, 9).solver == 1
+    assert bundle_entropy._make_cfg("rl", "pc", 5, None, None, 0, 6, 6).line_search == 1
+    assert bundle_entropy._make_cfg("dual", "pc", 10, None, None, 0, 8, 9).line_search == 0
+
+
+def test_dropin_module_names_exist():
+    import importlib.util
+    for sub in ("dropin", "dropin_rl"):
+        path = os.path.join(ROOT, "icnn_b200", sub, "bundle_entropy.py")
+        assert os.path.exists(path)
+        spec = importlib.util.spec_from_file_location("bundle_entropy_" + sub, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        assert callable(mod.solveBatch)

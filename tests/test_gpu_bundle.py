@@ -1,0 +1,252 @@
+"""K2 / fused-loop parity on the GPU against the numpy oracle and the reference-generated
+golden vectors.
+
+Tolerances (stated per test):
+  * K2 in isolation -- the oracle and the GPU are fed bit-identical float32-representable (f, g):
+    Mehrotra-PC and dual-Newton modes are restatements of the same float64 algorithm, asserted
+    at 1e-9 on y* with identical active-set sizes and nIters;
+  * fused (float32 K1) vs the float64 oracle -- the north-star tolerance 1e-4 on y* at the
+    reference's short horizons (5 / 10 iterations); at long horizons the oracle itself moves by
+    more than 1e-4 under float32 rounding of f, g (SURVEY.md section 7 hard part 1), so the assertion
+    is "GPU-vs-oracle no worse than oracle(float32 fg)-vs-oracle(float64 fg)" plus a median bound.
+"""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bundle_np, picnn_np, synth
+
+pytestmark = pytest.mark.gpu
+np.seterr(all="ignore")
+
+
+def r32(fg):
+    def w(y):
+        f, g = fg(y)
+        return f.astype(np.float32).astype(np.float64), g.astype(np.float32).astype(np.float64)
+    return w
+
+
+def rowdiff(a, b):
+    return np.abs(a - b).max(axis=1)
+
+
+def lens(rows):
+    return np.array([len(r) for r in rows])
+
+
+K2_CASES = [("C1", 64, 5), ("C1", 13, 20), ("C3", 24, 10), ("T", 12, 10), ("C5", 3, 6)]
+
+
+@pytest.mark.parametrize("name,B,nIter", K2_CASES)
+def test_k2_pc_matches_oracle(name, B, nIter):
+    from icnn_b200 import bundle_entropy as be
+    cfg = synth.CONFIGS[name]
+    p, x, y0 = synth.make_inputs(name, B=B)
+    fg = r32(picnn_np.make_fg(p, x))
+    o = bundle_np.solve_batch(fg, y0.copy(), nIter=nIter, variant="lib", solver="pc")
+    r = be.solveBatch(fg, y0.copy(), nIter=nIter, solver="pc", variant="lib")
+    same = (lens(r[1]) == lens(o[1])) & (np.array(r[5]) == np.array(o[5]))
+    assert same.mean() >= 0.95          # a rank-stop decision may flip on a near-dependent row
+    assert rowdiff(r[0], o[0])[same].max() < 1e-9
+    assert rowdiff(r[0], o[0]).max() < 1e-4
+    for u in np.flatnonzero(same)[:8]:
+        k = len(o[1][u])
+        if k:
+            np.testing.assert_allclose(r[3][u], o[3][u], atol=1e-8)
+            np.testing.assert_allclose(np.array(r[2][u]), np.array(o[2][u]), atol=1e-9)
+            np.testing.assert_allclose(np.array(r[1][u]), np.array(o[1][u]), atol=0)
+            np.testing.assert_allclose(np.array(r[4][u]), np.array(o[4][u]), atol=1e-9)
+
+
+@pytest.mark.parametrize("name,B,nIter", K2_CASES[:4])
+def test_k2_dual_matches_oracle(name, B, nIter):
+    from icnn_b200 import bundle_entropy as be
+    p, x, y0 = synth.make_inputs(name, B=B)
+    fg = r32(picnn_np.make_fg(p, x))
+    o = bundle_np.solve_batch(fg, y0.copy(), nIter=nIter, variant="dual")
+    r = be.solveBatch(fg, y0.copy(), nIter=nIter, variant="dual")
+    same = (lens(r[1]) == lens(o[1])) & (np.array(r[5]) == np.array(o[5]))
+    assert same.mean() >= 0.95
+    assert rowdiff(r[0], o[0])[same].max() < 1e-9
+    # invariants: lam on the simplex, y = sigma(-G^T lam) for unfinished samples
+    for u in range(B):
+        lam = r[3][u]
+        if lam is None:
+            continue
+        assert np.all(lam > 0) and abs(lam.sum() - 1) < 1e-9
+        if r[5][u] == nIter:
+            y = 1.0 / (1.0 + np.exp(np.array(r[1][u], dtype=np.float64).T.dot(lam)))
+            np.testing.assert_allclose(y, r[0][u], atol=1e-12)
+
+
+@pytest.mark.parametrize("B,nIter", [(256, 5), (40, 12)])
+def test_k2_rl_matches_oracle(B, nIter):
+    from icnn_b200 import bundle_entropy as be
+    p, x, y0 = synth.make_inputs("C4", B=B)
+    fg = r32(picnn_np.make_fg(p, x, affine=True))
+    calls = []
+    o = bundle_np.solve_batch(fg, y0.copy(), nIter=nIter, variant="rl")
+    r = be.solveBatch(fg, y0.copy(), nIter=nIter, variant="rl", callback=lambda t, f: calls.append((t, f.shape)))
+    assert r[0].min() >= 0.03 and r[0].max() <= 0.97          # RL/src/bundle_entropy.py:118
+    assert rowdiff(r[0], o[0]).max() < 1e-5
+    assert np.median(rowdiff(r[0], o[0])) < 1e-8
+    assert calls and calls[0] == (0, (B,))                     # callback(t, fi), :103-104
+
+
+GOLD = [("c1_pc", 1e-5, 1e-7), ("c1_dual", 1e-5, 1e-7), ("c1_rl", 1e-5, 1e-6), ("c1_boyd", None, None),
+        ("c1_pc_long", 1e-5, 1e-7), ("c3_pc", None, 1e-5), ("c3_dual", None, 1e-5), ("c4_rl", 1e-5, 1e-6),
+        ("c4_rl_long", 1e-4, 1e-6), ("t_pc", 1e-4, 1e-5), ("t_dual", 1e-4, 1e-5), ("c2_pc", None, 1e-3),
+        ("c5_pc", 1e-4, 1e-5)]
+
+
+@pytest.mark.parametrize("case,maxtol,medtol", GOLD)
+def test_k2_against_reference_golden(case, maxtol, medtol, golden_dir):
+    """GPU bundle step driven by the float64 oracle fg (rounded to float32 on upload) vs the
+    outputs of the UNMODIFIED reference modules on the same inputs."""
+    from icnn_b200 import bundle_entropy as be
+    gold = np.load(os.path.join(golden_dir, case + ".npz"))
+    cfgname = str(gold["config"])
+    cfg = synth.CONFIGS[cfgname]
+    B, nIter, variant = int(gold["B"]), int(gold["nIter"]), str(gold["variant"])
+    p, x, y0 = synth.make_inputs(cfgname, B=B)
+    fg = picnn_np.make_fg(p, x, affine=cfg["affine"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r = be.solveBatch(fg, y0.copy(), nIter=nIter, variant=variant, solver=str(gold["solver"]) or "pc")
+    d = rowdiff(r[0], gold["x"])
+    if case == "c1_boyd":
+        # 'boyd' is accepted and mapped to the converged solve; the reference's 20 damped
+        # iterations stop short of the optimum, so only closeness of the objective is asked
+        fgv = lambda y: fg(y)[0] + np.sum(y * np.log(y) + (1 - y) * np.log(1 - y), axis=1)  # noqa: E731
+        assert np.all(fgv(r[0]) <= fgv(gold["x"]) + 1e-6)
+        return
+    if maxtol is not None:
+        assert d.max() < maxtol, (d.max(), np.median(d))
+    assert np.median(d) < medtol, np.median(d)
+    agree = np.mean(lens(r[1]) == gold["counts"])
+    assert agree >= (0.5 if nIter > 10 else 0.8), agree
+
+
+FUSED = [("C1", 64, 5, 1e-4), ("C4", 512, 5, 1e-4), ("T", 48, 10, 1e-4), ("C3", 96, 10, None), ("C2", 6, 30, None)]
+
+
+@pytest.mark.parametrize("name,B,nIter,maxtol", FUSED)
+def test_fused_vs_oracle(name, B, nIter, maxtol):
+    """The headline parity statement: fused device loop (float32 K1 + float64 K2) vs the float64
+    oracle of the variant BASELINE.json names, next to the oracle's own float32 noise floor."""
+    import icnn_b200
+    from icnn_b200 import bundle_entropy as be
+    cfg = synth.CONFIGS[name]
+    p, x, y0 = synth.make_inputs(name, B=B)
+    variant = cfg["variant"]
+    o = bundle_np.solve_batch(picnn_np.make_fg(p, x, affine=cfg["affine"]), y0.copy(), nIter=nIter, variant=variant)
+    o32 = bundle_np.solve_batch(picnn_np.make_fg(p, x, affine=cfg["affine"], dtype=np.float32, out_dtype=np.float64),
+                                y0.copy(), nIter=nIter, variant=variant)
+    net = icnn_b200.PICNN.from_params(p)
+    y0c = y0.copy()
+    r = be.solveBatch(net.bind(x, affine=cfg["affine"]), y0c, nIter=nIter, variant=variant)
+    assert r[0] is y0c                                       # initXs is overwritten in place (:200)
+    d = rowdiff(r[0], o[0])
+    floor = rowdiff(o32[0], o[0])
+    print("\n%s: GPU-vs-oracle max %.2e median %.2e frac>1e-4 %.3f | oracle f32 noise floor max %.2e median %.2e frac>1e-4 %.3f"
+          % (name, d.max(), np.median(d), np.mean(d > 1e-4), floor.max(), np.median(floor), np.mean(floor > 1e-4)))
+    if maxtol is not None:
+        assert d.max() < maxtol
+    else:
+        assert np.median(d) < max(1e-5, 4 * np.median(floor))
+        assert np.mean(d > 1e-4) <= np.mean(floor > 1e-4) + 0.1
+    # objective gap: f - H at the GPU solution is as good as the oracle's
+    fg64 = picnn_np.make_fg(p, x, affine=cfg["affine"])
+    obj = lambda y: fg64(y)[0] + np.sum(y * np.log(y) + (1 - y) * np.log(1 - y), axis=1)  # noqa: E731
+    gap = obj(r[0]) - obj(o[0])
+    assert np.median(np.abs(gap)) < 1e-5 and gap.max() < 5e-3
+
+
+def test_shard_concat_equals_unsharded():
+    """Samples are independent: solving two row blocks separately is bit-identical to solving
+    the batch at once (what the multi-GPU sharding relies on)."""
+    import icnn_b200
+    from icnn_b200 import bundle_entropy as be
+    p, x, y0 = synth.make_inputs("C3", B=80)
+    net = icnn_b200.PICNN.from_params(p)
+    full = be.solveBatch(net.bind(x), y0.copy(), nIter=10)
+    a = be.solveBatch(net.bind(x[:37]), y0[:37].copy(), nIter=10)
+    b = be.solveBatch(net.bind(x[37:]), y0[37:].copy(), nIter=10)
+    np.testing.assert_array_equal(full[0], np.concatenate([a[0], b[0]]))
+    assert full[5] == a[5] + b[5]
+
+
+def test_fused_properties_at_full_size():
+    """Config 3 at BASELINE.json's full size (B=4096, n=159, 10 iterations): size-independent
+    properties -- multipliers on the simplex, bundle rows under-estimate the convex f at y*,
+    rows are the gradients at the stored iterates, y* inside the box."""
+    import icnn_b200
+    from icnn_b200 import bundle_entropy as be
+    p, x, y0 = synth.make_inputs("C3")
+    net = icnn_b200.PICNN.from_params(p)
+    fg = net.bind(x)
+    y, G, h, lam, ys, nIters = be.solveBatch(fg, y0.copy(), nIter=10)
+    assert y.shape == (4096, 159) and np.all(np.isfinite(y)) and y.min() > 0 and y.max() < 1
+    f_star, _ = fg(y)
+    for u in range(0, 4096, 97):
+        k = len(G[u])
+        assert 1 <= k <= 10 and len(h[u]) == k and len(ys[u]) == k and lam[u].shape == (k,)
+        assert np.all(lam[u] > 1e-8) and abs(lam[u].sum() - 1) < 1e-6
+        Gu = np.array(G[u], dtype=np.float64)
+        assert np.all(Gu.dot(y[u]) + np.array(h[u]) <= f_star[u] + 1e-3 * max(1, abs(f_star[u])))
+    # rows are gradients at the stored iterates (consistency of A / xs, multi-label-cls/icnn_ebundle.py:300-305)
+    us = list(range(0, 4096, 512))
+    Y = np.stack([ys[u][-1] for u in us])
+    _, gchk = net.bind(x[us])(Y)
+    for i, u in enumerate(us):
+        np.testing.assert_allclose(G[u][-1], gchk[i], rtol=1e-4, atol=1e-5)
+
+
+def test_edge_cases_and_error_paths():
+    import icnn_b200
+    from icnn_b200 import bundle_entropy as be
+    p, x, y0 = synth.make_inputs("C1", B=9)
+    net = icnn_b200.PICNN.from_params(p)
+    fg = net.bind(x)
+    # nIter = 1: one row, y = PC solution of a single cut; compare with the oracle
+    r = be.solveBatch(fg, y0.copy(), nIter=1)
+    o = bundle_np.solve_batch(picnn_np.make_fg(p, x), y0.copy(), nIter=1)
+    assert rowdiff(r[0], o[0]).max() < 1e-5 and r[5] == o[5]
+    # B = 1
+    r1 = be.solveBatch(net.bind(x[:1]), y0[:1].copy(), nIter=5)
+    np.testing.assert_allclose(r1[0], be.solveBatch(fg, y0.copy(), nIter=5)[0][:1], atol=0)
+    # unknown solver -> RuntimeError like lib/bundle_entropy.py:232
+    with pytest.raises(RuntimeError, match="Solver unknown"):
+        be.solveBatch(fg, y0.copy(), solver="nope")
+    # callback(t, f, x) is invoked once per executed iteration with the live iterate
+    seen = []
+    be.solveBatch(fg, y0.copy(), nIter=5, callback=lambda t, f, xx: seen.append((t, f.shape, xx.shape)))
+    assert seen[0] == (0, (9,), (9, 8)) and [s[0] for s in seen] == list(range(len(seen)))
+    # non-finite fg: flagged, not propagated silently
+    def bad(y):
+        f, g = picnn_np.make_fg(p, x)(y)
+        g[3, 2] = np.nan
+        return f, g
+    with pytest.warns(UserWarning, match="non-finite"):
+        rb = be.solveBatch(bad, y0.copy(), nIter=3, return_state=True)
+    assert rb[-1].status_host[3] == 4 and np.all(np.isfinite(rb[0][[0, 1, 2, 4]]))
+    with pytest.raises(RuntimeError):
+        be.solveBatch(bad, y0.copy(), nIter=3, strict=True)
+
+
+def test_early_exit_when_all_finished():
+    """Once every sample hit the rank stop the remaining iterations are device-side no-ops
+    (the reference returns early, lib/bundle_entropy.py:239)."""
+    import icnn_b200
+    from icnn_b200 import bundle_entropy as be
+    p, x, y0 = synth.make_inputs("C1", B=16)
+    net = icnn_b200.PICNN.from_params(p)
+    r = be.solveBatch(net.bind(x), y0.copy(), nIter=40, return_state=True)
+    na = r[-1].nactive.cpu().numpy()
+    o = bundle_np.solve_batch(picnn_np.make_fg(p, x), y0.copy(), nIter=40)
+    assert na[0] == 16 and na[-1] == 0 and max(r[5]) < 39
+    assert rowdiff(r[0], o[0]).max() < 1e-4

@@ -1,0 +1,62 @@
+"""K1 parity on the GPU: PICNN f / df/dy (and the momentum-GD loop built on it) against the
+float64 numpy oracle.  Tolerance: the kernel computes in float32 (FFMA), the oracle in float64;
+measured max relative error is ~1e-6, asserted at 1e-5 (the 1e-4 target on y* is on the
+iterate, tested in test_gpu_bundle.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import picnn_np, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _net(name, B):
+    import icnn_b200
+    cfg = synth.CONFIGS[name]
+    p, x, y0 = synth.make_inputs(name, B=B)
+    return cfg, p, x, y0, icnn_b200.PICNN.from_params(p)
+
+
+@pytest.mark.parametrize("name,B", [("C1", 64), ("C1", 1), ("C3", 77), ("C4", 300), ("T", 130), ("C5", 5)])
+def test_fg_matches_oracle(name, B):
+    cfg, p, x, y0, net = _net(name, B)
+    fg = net.bind(x, affine=cfg["affine"])
+    y = np.random.RandomState(11).uniform(0.02, 0.98, size=y0.shape).astype(np.float32).astype(np.float64)
+    f, g = fg(y)
+    fo, go = picnn_np.make_fg(p, x, affine=cfg["affine"])(y)
+    assert f.dtype == np.float32 and g.dtype == np.float32 and g.shape == y.shape
+    assert np.abs(f - fo).max() <= 1e-5 * max(1.0, np.abs(fo).max())
+    assert np.abs(g - go).max() <= 1e-5 * max(1.0, np.abs(go).max())
+
+
+def test_fg_is_row_independent():
+    """A row's result does not depend on which other rows share its tile (needed for
+    shard + concat == unsharded)."""
+    cfg, p, x, y0, net = _net("C3", 96)
+    y = np.random.RandomState(5).uniform(0.1, 0.9, size=y0.shape)
+    f, g = net.bind(x)(y)
+    f2, g2 = net.bind(x[37:70])(y[37:70])
+    np.testing.assert_array_equal(f[37:70], f2)
+    np.testing.assert_array_equal(g[37:70], g2)
+
+
+@pytest.mark.parametrize("name,B,lr,mom", [("C1", 64, 0.01, 0.3), ("C3", 50, 0.01, 0.3), ("T", 40, 0.01, 0.9)])
+def test_momentum_gd_matches_oracle(name, B, lr, mom):
+    """multi-label-cls/icnn-back.py:116-131 defaults (.01, .3, 30) and completion's (.01, .9)."""
+    import icnn_b200
+    cfg, p, x, y0, net = _net(name, B)
+    fg = net.bind(x)
+    y, f = icnn_b200.gd.solve(fg, y0, nIter=30, lr=lr, momentum=mom)
+    yo, fo = picnn_np.momentum_gd(picnn_np.make_fg(p, x), y0, 30, lr, mom)
+    assert np.abs(y - yo).max() < 2e-5
+    assert np.abs(f - fo).max() <= 2e-5 * max(1.0, np.abs(fo).max())
+
+
+def test_gd_zero_iterations_returns_energy_of_y0():
+    import icnn_b200
+    cfg, p, x, y0, net = _net("C1", 8)
+    y, f = icnn_b200.gd.solve(net.bind(x), y0, nIter=0)
+    np.testing.assert_allclose(y, y0, atol=0)
+    fo, _ = picnn_np.make_fg(p, x)(y0)
+    np.testing.assert_allclose(f, fo, rtol=1e-5, atol=1e-5)
