@@ -81,6 +81,26 @@ def _cpu_worker(args):
     return (hi - lo) * iters[0], dt
 
 
+def usable_cores():
+    """Host cores this process may really use: min(affinity mask, cgroup v2/v1 CPU quota)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    for path, parse in (("/sys/fs/cgroup/cpu.max", lambda t: t.split()),
+                        ("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", lambda t: [t.strip(), open(
+                            "/sys/fs/cgroup/cpu/cpu.cfs_period_us").read().strip()])):
+        try:
+            q, per = parse(open(path).read())
+            if q != "max" and int(q) > 0:
+                n = min(n, max(1, int(int(q) / int(per))))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
 _POOL = {}
 
 
@@ -120,7 +140,7 @@ def cpu_baseline(workload, budget_s=15.0):
     """Bounded sample sized for ~budget_s seconds on all host cores."""
     from icnn_b200 import workloads
     cfg = workloads.CONFIGS[workload]
-    procs = os.cpu_count() or 1
+    procs = usable_cores()
     # calibrate on a tiny sample (one row per process, few iterations are not representative:
     # cost grows with the bundle, so calibrate with the full iteration count on 1 row/proc)
     cal_rows = min(cfg["B"], procs)
@@ -368,7 +388,7 @@ def run_reference(args):
         return
     from icnn_b200 import workloads
     cfg = workloads.CONFIGS[args.workload]
-    procs = os.cpu_count() or 1
+    procs = usable_cores()
     # bounded sample per step, sized from one calibration run so K+W steps end within minutes
     cal_rows = min(cfg["B"], procs)
     s0, w0 = cpu_reference(args.workload, cal_rows, procs)

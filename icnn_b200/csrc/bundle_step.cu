@@ -16,6 +16,8 @@
 //   gram pass   : warp owns 4x4 blocks of the k x k output ->  G diag(w) G^T         (shuffle reduce)
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace icnn {
 
 struct StepArgs {
@@ -97,46 +99,76 @@ struct Grp {
 
 // ---- k x k dense algebra, executed by ONE warp (lane-parallel over rows), FP64 in smem -------
 
-// In-place lower Cholesky of the symmetric matrix A (full storage, leading dim ld).
-// Returns false on a non-positive / non-finite pivot.  minpiv (optional) gets the last pivot.
-__device__ inline bool warp_cholesky(double* A, int k, int ld, int lane, double* last_pivot) {
+// In-place lower Cholesky of the symmetric matrix A (full storage, leading dim ld), left-looking,
+// lane r owns rows r and r+32.  invd[c] = 1 / L[c][c].  Returns false on a non-positive /
+// non-finite pivot.  One __syncwarp per column; pivots travel by shuffle, not shared memory.
+__device__ inline bool warp_cholesky(double* A, double* invd, int k, int ld, int lane) {
   bool ok = true;
+  const int r0 = lane, r1 = lane + 32;
   for (int c = 0; c < k; ++c) {
-    // s_r = A[r][c] - sum_{p<c} L[r][p] L[c][p]   for r >= c
-    for (int r = c + lane; r < k; r += 32) {
-      double s = A[r * ld + c];
-      for (int p = 0; p < c; ++p) s -= A[r * ld + p] * A[c * ld + p];
-      A[r * ld + c] = s;
+    double s0 = 0.0, s1 = 0.0;
+    if (r0 >= c && r0 < k) {
+      s0 = A[r0 * ld + c];
+      for (int p = 0; p < c; ++p) s0 = fma(-A[r0 * ld + p], A[c * ld + p], s0);
     }
-    __syncwarp();
-    const double piv = A[c * ld + c];
-    if (c == k - 1 && last_pivot) *last_pivot = piv;
+    if (r1 >= c && r1 < k) {
+      s1 = A[r1 * ld + c];
+      for (int p = 0; p < c; ++p) s1 = fma(-A[r1 * ld + p], A[c * ld + p], s1);
+    }
+    const double piv = __shfl_sync(0xffffffffu, (c < 32) ? s0 : s1, c & 31);
     if (!(piv > 0.0) || !isfinite(piv)) { ok = false; break; }
-    const double d = sqrt(piv);
-    __syncwarp();
-    for (int r = c + lane; r < k; r += 32) A[r * ld + c] = (r == c) ? d : A[r * ld + c] / d;
+    const double inv = rsqrt(piv);
+    if (r0 > c && r0 < k) A[r0 * ld + c] = s0 * inv;
+    if (r1 > c && r1 < k) A[r1 * ld + c] = s1 * inv;
+    if (lane == 0) { A[c * ld + c] = piv * inv; invd[c] = inv; }
     __syncwarp();
   }
   __syncwarp();
   return ok;
 }
 
-// Solve L L^T x = b in place (b -> x), L lower from warp_cholesky.  One warp.
-__device__ inline void warp_chol_solve(const double* L, int k, int ld, double* b, int lane) {
-  for (int i = 0; i < k; ++i) {  // forward
-    const double xi = b[i] / L[i * ld + i];
-    __syncwarp();
-    for (int r = i + 1 + lane; r < k; r += 32) b[r] -= L[r * ld + i] * xi;
-    if (lane == 0) b[i] = xi;
-    __syncwarp();
+// Solve L L^T X = B in place for NR right-hand sides held in shared memory (rhs[q][0..k)).
+// The running vectors live in registers (lane r owns rows r, r+32) and the pivots are broadcast
+// by shuffle, so a substitution step costs one shuffle + one FMA of latency instead of two
+// shared-memory round trips.
+template <int NR>
+__device__ inline void warp_chol_solve(const double* L, const double* invd, int k, int ld,
+                                       double* const (&rhs)[NR], int lane) {
+  const int r0 = lane, r1 = lane + 32;
+  double b0[NR], b1[NR];
+#pragma unroll
+  for (int q = 0; q < NR; ++q) {
+    b0[q] = (r0 < k) ? rhs[q][r0] : 0.0;
+    b1[q] = (r1 < k) ? rhs[q][r1] : 0.0;
   }
-  for (int i = k - 1; i >= 0; --i) {  // backward with L^T
-    const double xi = b[i] / L[i * ld + i];
-    __syncwarp();
-    for (int r = lane; r < i; r += 32) b[r] -= L[i * ld + r] * xi;
-    if (lane == 0) b[i] = xi;
-    __syncwarp();
+  for (int i = 0; i < k; ++i) {  // forward: L x = b
+    const double di = invd[i];
+    const double l0 = (r0 > i && r0 < k) ? L[r0 * ld + i] : 0.0;
+    const double l1 = (r1 > i && r1 < k) ? L[r1 * ld + i] : 0.0;
+#pragma unroll
+    for (int q = 0; q < NR; ++q) {
+      const double xi = __shfl_sync(0xffffffffu, (i < 32) ? b0[q] : b1[q], i & 31) * di;
+      b0[q] = (r0 == i) ? xi : fma(-l0, xi, b0[q]);
+      b1[q] = (r1 == i) ? xi : fma(-l1, xi, b1[q]);
+    }
   }
+  for (int i = k - 1; i >= 0; --i) {  // backward: L^T x = b
+    const double di = invd[i];
+    const double l0 = (r0 < i) ? L[i * ld + r0] : 0.0;
+    const double l1 = (r1 < i) ? L[i * ld + r1] : 0.0;
+#pragma unroll
+    for (int q = 0; q < NR; ++q) {
+      const double xi = __shfl_sync(0xffffffffu, (i < 32) ? b0[q] : b1[q], i & 31) * di;
+      b0[q] = (r0 == i) ? xi : fma(-l0, xi, b0[q]);
+      b1[q] = (r1 == i) ? xi : fma(-l1, xi, b1[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NR; ++q) {
+    if (r0 < k) rhs[q][r0] = b0[q];
+    if (r1 < k) rhs[q][r1] = b1[q];
+  }
+  __syncwarp();
 }
 
 // step length keeping v + a dv >= 0  (lib/bundle_entropy.py:158-163), over a k-vector, one warp
@@ -155,6 +187,39 @@ __device__ __forceinline__ double softplus_d(double x) {  // lib/bundle_entropy_
 }
 
 // ---- G passes -----------------------------------------------------------------------------
+
+constexpr int CH = 8;  // columns per thread per chunk in a column pass
+
+// column pass core: acc[c] = sum_j G_j[e_c] * w[j] for this thread's CH columns
+// e_c = base + c*T + tid.  The row loop is outermost so w[j] and the row pointer are read from
+// shared memory once per CH global loads.
+template <int T>
+__device__ __forceinline__ void col_dots(const float* const* rowp, int k, int n, int base, int tid,
+                                         const double* w, double (&acc)[CH]) {
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] = 0.0;
+  if (base + CH * T <= n) {
+    for (int j = 0; j < k; ++j) {
+      const float* p = rowp[j] + base + tid;
+      const double wj = w[j];
+      float v[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) v[c] = __ldg(p + c * T);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[c] = fma((double)v[c], wj, acc[c]);
+    }
+  } else {
+    for (int j = 0; j < k; ++j) {
+      const float* p = rowp[j] + base + tid;
+      const double wj = w[j];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const float v = (base + c * T + tid < n) ? __ldg(p + c * T) : 0.f;
+        acc[c] = fma((double)v, wj, acc[c]);
+      }
+    }
+  }
+}
 
 // gram pass: M[i][j] = sum_e w[e] G_i[e] G_j[e] (symmetric fill), w == nullptr -> 1
 template <int WPS>
@@ -202,18 +267,19 @@ __device__ inline void gram_pass(const Grp<WPS>& g, const float* const* rowp, in
 
 // ---- the step kernel ----------------------------------------------------------------------
 
-template <int WPS>
-__global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
+template <int WPS, int MINB>
+__global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
   const icnn_bundle_bufs& b = A.b;
   const icnn_bundle_cfg& cf = A.c;
   if (b.nactive[A.t] == 0) return;
   extern __shared__ double smem_d[];
   constexpr int GPB = 8 / WPS;  // groups per block
+  constexpr int T = WPS * 32;
   Grp<WPS> g;
-  g.tid = threadIdx.x % (WPS * 32);
+  g.tid = threadIdx.x % T;
   g.lane = threadIdx.x & 31;
   g.warp = g.tid >> 5;
-  g.gid = threadIdx.x / (WPS * 32);
+  g.gid = threadIdx.x / T;
   const int u = blockIdx.x * GPB + g.gid;
   if (u >= b.B) return;
   if (b.finished[u]) return;
@@ -235,7 +301,7 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
   double* dza = kv + 6 * KS;
   double* dsa = kv + 7 * KS;
   double* dzc = kv + 8 * KS;
-  double* dsc = kv + 9 * KS;
+  double* invd = kv + 9 * KS;   // 1 / diag(L)
   double* w1 = kv + 10 * KS;
   double* ck = kv + 11 * KS;
   double* gk = kv + 12 * KS;   // gradient
@@ -245,7 +311,7 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
   double* yk = kv + 16 * KS;   // change of variables y (lambda with pivot set to 1)
   double* ek = kv + 17 * KS;   // e vector
   double* tk = kv + 18 * KS;   // temp
-  const float** rowp = reinterpret_cast<const float**>(kv + 19 * KS);  // row pointers (k+1 <= KS)
+  const float** rowp = reinterpret_cast<const float**>(kv + 19 * KS);  // row pointers (k <= KS)
   g.red = kv + (size_t)NKVEC * KS;
   double* sc = g.red + 4 * WPS;  // 16 scalars
   int* isc = reinterpret_cast<int*>(sc + 12);  // 8 ints
@@ -261,7 +327,7 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
   double* yu = b.y + (size_t)u * n;
   const int slot_new = permu[k0];
 
-  for (int j = g.tid; j < k; j += g.T) rowp[j] = Gu + (size_t)permu[j] * n;
+  for (int j = g.tid; j < k; j += T) rowp[j] = Gu + (size_t)permu[j] * n;
   if (g.tid == 0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) isc[i] = 0;
@@ -273,10 +339,9 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
   {
     double hs = 0.0, rs = 0.0, bad = 0.0;
     double* ysrow = b.ys ? b.ys + ((size_t)u * KS + slot_new) * n : nullptr;
-    for (int e = g.tid; e < n; e += g.T) {
+    for (int e = g.tid; e < n; e += T) {
       const double ge = (double)gnew[e];
       const double ye = yu[e];
-      yv[e] = ye;
       hs = fma(ge, ye, hs);
       rs += ge;
       if (!isfinite(ge)) bad = 1.0;
@@ -308,27 +373,29 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
     g.sync();
   }
   // NOTE: control flow below is group-uniform: every decision is read from shared memory after
-  // a group barrier.
+  // a group barrier (or is the result of a group-wide reduction).
   bool dependent = false;
   if (cf.variant != ICNN_VARIANT_RL) {
     // ---- dependency test (stands in for np.linalg.matrix_rank, lib/bundle_entropy.py:219) ----
-    // distance of the new row from the span of the active rows, computed explicitly with one
-    // step of iterative refinement, relative to the largest row norm.
+    // distance of the new row from the span of the active rows, computed explicitly (with one
+    // step of iterative refinement in the gray zone), relative to the largest row norm.
     if (k > n) dependent = true;
     else if (k0 > 0) {
       if (g.warp == 0) {
         for (int i = g.lane; i < k0; i += 32)
           for (int j = 0; j < k0; ++j) Lm[i * ld + j] = gramu[(size_t)permu[i] * KS + permu[j]];
-        for (int j = g.lane; j < k0; j += 32) { rk[j] = tk[j]; }
+        for (int j = g.lane; j < k0; j += 32) rk[j] = tk[j];
         __syncwarp();
-        const bool ok = warp_cholesky(Lm, k0, ld, g.lane, nullptr);
-        if (ok) warp_chol_solve(Lm, k0, ld, rk, g.lane);
-        if (g.lane == 0) isc[1] = ok ? 1 : 0;
+        const bool ok = warp_cholesky(Lm, invd, k0, ld, g.lane);
+        if (ok) { double* const r1[1] = {rk}; warp_chol_solve<1>(Lm, invd, k0, ld, r1, g.lane); }
+        double md = tk[k0];
+        for (int j = g.lane; j < k0; j += 32) md = fmax(md, gramu[(size_t)permu[j] * KS + permu[j]]);
+        md = Grp<1>::wmax(md);
+        if (g.lane == 0) { isc[1] = ok ? 1 : 0; sc[9] = md; }
         __syncwarp();
       }
       g.sync();
-      double maxdiag = tk[k0];
-      for (int j = 0; j < k0; ++j) maxdiag = fmax(maxdiag, gramu[(size_t)permu[j] * KS + permu[j]]);
+      const double maxdiag = sc[9];
       if (isc[0]) dependent = true;          // exact duplicate of an active row
       else if (!isc[1]) dependent = true;    // active rows themselves numerically dependent
       else {
@@ -336,11 +403,18 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
         for (int rep = 0; rep < 2; ++rep) {
           // residual res = (rep ? res : gnew) - sum_j c_j G_j
           double p = 0.0;
-          for (int e = g.tid; e < n; e += g.T) {
-            double r = rep ? rv[e] : (double)gnew[e];
-            for (int j = 0; j < k0; ++j) r = fma(-rk[j], (double)__ldg(rowp[j] + e), r);
-            rv[e] = r;
-            p = fma(r, r, p);
+          for (int cb = 0; cb < n; cb += CH * T) {
+            double acc[CH];
+            col_dots<T>(rowp, k0, n, cb, g.tid, rk, acc);
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+              const int e = cb + c * T + g.tid;
+              if (e < n) {
+                const double r = (rep ? rv[e] : (double)gnew[e]) - acc[c];
+                rv[e] = r;
+                p = fma(r, r, p);
+              }
+            }
           }
           p = g.sum(p);
           if (p <= thr2) { dependent = true; break; }
@@ -355,7 +429,7 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
             if (g.lane == 0) rk[j] = acc;
           }
           g.sync();
-          if (g.warp == 0) warp_chol_solve(Lm, k0, ld, rk, g.lane);
+          if (g.warp == 0) { double* const r1[1] = {rk}; warp_chol_solve<1>(Lm, invd, k0, ld, r1, g.lane); }
           g.sync();
         }
       }
@@ -369,11 +443,11 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
     }
   }
   // commit the Gram row
-  for (int j = g.tid; j < k; j += g.T) {
+  for (int j = g.tid; j < k; j += T) {
     gramu[(size_t)slot_new * KS + permu[j]] = tk[j];
     gramu[(size_t)permu[j] * KS + slot_new] = tk[j];
   }
-  for (int j = g.tid; j < k; j += g.T) hk[j] = hu[permu[j]];  // permu[k0] == slot_new
+  for (int j = g.tid; j < k; j += T) hk[j] = hu[permu[j]];  // permu[k0] == slot_new
   g.sync();
 
   int inner_its = 0;
@@ -382,97 +456,106 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
   if (cf.solver == ICNN_SOLVER_PC) {
     // =====================  Mehrotra predictor-corrector, lib/bundle_entropy.py:5-78  ==========
     const int maxit = cf.max_inner > 0 ? cf.max_inner : 20;
-    for (int e = g.tid; e < n; e += g.T) yv[e] = 0.5;
-    for (int j = g.tid; j < k; j += g.T) { zk[j] = 1.0 / k; sk[j] = 1.0; }
+    for (int e = g.tid; e < n; e += T) yv[e] = 0.5;
+    for (int j = g.tid; j < k; j += T) { zk[j] = 1.0 / k; sk[j] = 1.0; }
     if (g.tid == 0) sc[0] = 1.0;  // t
     g.sync();
     for (int it = 0; it < maxit; ++it) {
-      // column pass: ry = log y - log(1-y) + G^T z
+      // column pass: ry = log y - log(1-y) + G^T z ; D = y(1-y) = 1/(1/y + 1/(1-y))
       double pr = 0.0;
-      for (int e = g.tid; e < n; e += g.T) {
-        double a = 0.0;
-        for (int j = 0; j < k; ++j) a = fma((double)__ldg(rowp[j] + e), zk[j], a);
-        const double ye = yv[e];
-        const double r = log(ye) - log(1.0 - ye) + a;
-        rv[e] = r;
-        pr = fma(r, r, pr);
+      for (int cb = 0; cb < n; cb += CH * T) {
+        double acc[CH];
+        col_dots<T>(rowp, k, n, cb, g.tid, zk, acc);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int e = cb + c * T + g.tid;
+          if (e < n) {
+            const double ye = yv[e];
+            const double r = log(ye) - log(1.0 - ye) + acc[c];
+            rv[e] = r;
+            dv[e] = ye * (1.0 - ye);
+            pr = fma(r, r, pr);
+          }
+        }
       }
-      pr = g.sum(pr);
-      // row pass: rd = G y + h - t + s ; q = G D ry     (D = y(1-y) = 1/(1/y + 1/(1-y)))
+      pr = g.sum(pr);   // (contains the barrier that publishes rv / dv)
+      if (WPS == 1) __syncwarp();
+      // row pass: rd = G y + h - t + s ; q = G D ry
       for (int j = g.warp; j < k; j += WPS) {
         const float* rj = rowp[j];
         double a1 = 0.0, a2 = 0.0;
         for (int e = g.lane; e < n; e += 32) {
-          const double ge = (double)__ldg(rj + e), ye = yv[e];
-          a1 = fma(ge, ye, a1);
-          a2 = fma(ge, ye * (1.0 - ye) * rv[e], a2);
+          const double ge = (double)__ldg(rj + e);
+          a1 = fma(ge, yv[e], a1);
+          a2 = fma(ge, dv[e] * rv[e], a2);
         }
         a1 = Grp<WPS>::wsum(a1);
         a2 = Grp<WPS>::wsum(a2);
         if (g.lane == 0) { rdk[j] = a1 + hk[j] - sc[0] + sk[j]; qk[j] = a2; }
       }
-      g.sync();
-      if (g.warp == 0) {
-        double zs = 0.0, dr = 0.0;
-        for (int j = g.lane; j < k; j += 32) { zs += zk[j]; dr = fma(rdk[j], rdk[j], dr); }
-        zs = Grp<1>::wsum(zs);
-        dr = Grp<1>::wsum(dr);
-        const double rt = 1.0 - zs;
-        if (g.lane == 0) {
-          sc[1] = rt;
-          isc[2] = (sqrt(pr + rt * rt) < 1e-8 && sqrt(dr) < 1e-8) ? 1 : 0;
-        }
-      }
-      g.sync();
-      if (isc[2]) break;
-      inner_its = it + 1;
-      // weights D into dv, then the weighted Gram
-      for (int e = g.tid; e < n; e += g.T) { const double ye = yv[e]; dv[e] = ye * (1.0 - ye); }
-      g.sync();
+      // weighted Gram (independent of the row pass: reads only G and dv)
       gram_pass<WPS>(g, rowp, k, n, dv, M, ld);
       g.sync();
       if (g.warp == 0) {
         const int lane = g.lane;
-        for (int j = lane; j < k; j += 32) M[j * ld + j] += sk[j] / zk[j];
-        __syncwarp();
-        for (int i = lane; i < k; i += 32)
-          for (int j = 0; j < k; ++j) Lm[i * ld + j] = M[i * ld + j];
-        __syncwarp();
-        const bool ok = warp_cholesky(Lm, k, ld, lane, nullptr);
-        if (!ok) { if (lane == 0) isc[3] = 1; }
-        else {
-          if (lane == 0) isc[3] = 0;
-          for (int j = lane; j < k; j += 32) w1[j] = 1.0;
+        double zs = 0.0, dr = 0.0;
+        for (int j = lane; j < k; j += 32) { zs += zk[j]; dr = fma(rdk[j], rdk[j], dr); }
+        zs = Grp<1>::wsum(zs);
+        dr = Grp<1>::wsum(dr);
+        const double rt = 1.0 - zs;
+        const bool conv = (sqrt(pr + rt * rt) < 1e-8 && sqrt(dr) < 1e-8);
+        if (conv) {
+          if (lane == 0) isc[2] = 1;
+        } else {
+          for (int i = lane; i < k; i += 32) {
+            for (int j = 0; j < k; ++j) Lm[i * ld + j] = M[i * ld + j];
+            Lm[i * ld + i] += sk[i] / zk[i];
+          }
           __syncwarp();
-          warp_chol_solve(Lm, k, ld, w1, lane);
-          double w1s = 0.0;
-          for (int j = lane; j < k; j += 32) w1s += w1[j];
-          w1s = Grp<1>::wsum(w1s);
-          // affine: r = rd - G D ry - (s/z) rc, rc = z  ->  r = rd - q - s
-          double rw = 0.0;
-          for (int j = lane; j < k; j += 32) { rk[j] = rdk[j] - qk[j] - sk[j]; rw = fma(rk[j], w1[j], rw); }
-          rw = Grp<1>::wsum(rw);
-          const double dt = (rw - sc[1]) / w1s;
-          for (int j = lane; j < k; j += 32) dza[j] = rk[j] - dt;
-          __syncwarp();
-          warp_chol_solve(Lm, k, ld, dza, lane);
-          for (int j = lane; j < k; j += 32) dsa[j] = -(sk[j] / zk[j]) * (zk[j] + dza[j]);
-          if (lane == 0) { sc[2] = dt; sc[3] = w1s; }
-          __syncwarp();
+          const bool ok = warp_cholesky(Lm, invd, k, ld, lane);
+          if (!ok) { if (lane == 0) isc[3] = 1; }
+          else {
+            // two right-hand sides in one sweep: w1 = M^-1 1, dza = M^-1 r with
+            // r = rd - G D ry - (s/z) rc, rc = z  ->  r = rd - q - s.   Then
+            // dt = (r.w1 - rt)/sum(w1) and dz_aff = M^-1 (r - dt 1) = M^-1 r - dt w1.
+            for (int j = lane; j < k; j += 32) { w1[j] = 1.0; dza[j] = rdk[j] - qk[j] - sk[j]; rk[j] = dza[j]; }
+            __syncwarp();
+            double* const r2[2] = {w1, dza};
+            warp_chol_solve<2>(Lm, invd, k, ld, r2, lane);
+            double w1s = 0.0, rw = 0.0;
+            for (int j = lane; j < k; j += 32) { w1s += w1[j]; rw = fma(rk[j], w1[j], rw); }
+            w1s = Grp<1>::wsum(w1s);
+            rw = Grp<1>::wsum(rw);
+            const double dt = (rw - rt) / w1s;
+            for (int j = lane; j < k; j += 32) {
+              dza[j] = fma(-dt, w1[j], dza[j]);
+              dsa[j] = -(sk[j] / zk[j]) * (zk[j] + dza[j]);
+            }
+            if (lane == 0) { sc[2] = dt; sc[3] = w1s; }
+          }
         }
+        __syncwarp();
       }
       g.sync();
+      if (isc[2]) break;
       if (isc[3]) { fail = 1; break; }
+      inner_its = it + 1;
       // column pass: dy_aff = -D (ry + G^T dz_aff) ; get_step(y, dy) and get_step(1-y, -dy)
       double st = 1e300, st2 = 1e300;
-      for (int e = g.tid; e < n; e += g.T) {
-        double a = 0.0;
-        for (int j = 0; j < k; ++j) a = fma((double)__ldg(rowp[j] + e), dza[j], a);
-        const double dy = -dv[e] * (rv[e] + a);
-        rv[e] = dy;  // rv now holds dy_aff
-        const double ye = yv[e];
-        if (dy < 0.0) st = fmin(st, -ye / dy);
-        if (dy > 0.0) st2 = fmin(st2, (1.0 - ye) / dy);
+      for (int cb = 0; cb < n; cb += CH * T) {
+        double acc[CH];
+        col_dots<T>(rowp, k, n, cb, g.tid, dza, acc);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int e = cb + c * T + g.tid;
+          if (e < n) {
+            const double dy = -dv[e] * (rv[e] + acc[c]);
+            rv[e] = dy;  // rv now holds dy_aff
+            const double ye = yv[e];
+            if (dy < 0.0) st = fmin(st, -ye / dy);
+            if (dy > 0.0) st2 = fmin(st2, (1.0 - ye) / dy);
+          }
+        }
       }
       st = g.min(st);
       st2 = g.min(st2);
@@ -492,22 +575,24 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
         const double sig = sg * sg * sg;
         const double mu = den / k;
         // corrector: ry = rt = rd = 0, rc = -(mu sig - ds_aff dz_aff)/s  ->  r = -(s/z) rc
-        double rw = 0.0;
         for (int j = lane; j < k; j += 32) {
           const double rc = -(mu * sig - dsa[j] * dza[j]) / sk[j];
           tk[j] = rc;
           rk[j] = -(sk[j] / zk[j]) * rc;
-          rw = fma(rk[j], w1[j], rw);
+          dzc[j] = rk[j];
         }
+        __syncwarp();
+        double* const r1[1] = {dzc};
+        warp_chol_solve<1>(Lm, invd, k, ld, r1, lane);   // dzc = M^-1 r
+        double rw = 0.0;
+        for (int j = lane; j < k; j += 32) rw = fma(rk[j], w1[j], rw);
         rw = Grp<1>::wsum(rw);
         const double dtc = rw / sc[3];
-        for (int j = lane; j < k; j += 32) dzc[j] = rk[j] - dtc;
-        __syncwarp();
-        warp_chol_solve(Lm, k, ld, dzc, lane);
         for (int j = lane; j < k; j += 32) {
-          dsc[j] = -(sk[j] / zk[j]) * (tk[j] + dzc[j]);
+          dzc[j] = fma(-dtc, w1[j], dzc[j]);      // M^-1 (r - dt_c 1)
+          const double dscj = -(sk[j] / zk[j]) * (tk[j] + dzc[j]);
           dza[j] += dzc[j];   // total dz
-          dsa[j] += dsc[j];   // total ds
+          dsa[j] += dscj;     // total ds
         }
         if (lane == 0) sc[2] += dtc;  // total dt
         __syncwarp();
@@ -515,14 +600,20 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
       g.sync();
       // column pass: dy = dy_aff - D G^T dz_cor ; step bounds
       st = 1e300; st2 = 1e300;
-      for (int e = g.tid; e < n; e += g.T) {
-        double a = 0.0;
-        for (int j = 0; j < k; ++j) a = fma((double)__ldg(rowp[j] + e), dzc[j], a);
-        const double dy = rv[e] - dv[e] * a;
-        rv[e] = dy;
-        const double ye = yv[e];
-        if (dy < 0.0) st = fmin(st, -ye / dy);
-        if (dy > 0.0) st2 = fmin(st2, (1.0 - ye) / dy);
+      for (int cb = 0; cb < n; cb += CH * T) {
+        double acc[CH];
+        col_dots<T>(rowp, k, n, cb, g.tid, dzc, acc);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int e = cb + c * T + g.tid;
+          if (e < n) {
+            const double dy = rv[e] - dv[e] * acc[c];
+            rv[e] = dy;
+            const double ye = yv[e];
+            if (dy < 0.0) st = fmin(st, -ye / dy);
+            if (dy > 0.0) st2 = fmin(st2, (1.0 - ye) / dy);
+          }
+        }
       }
       st = g.min(st);
       st2 = g.min(st2);
@@ -531,13 +622,14 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
         const int lane = g.lane;
         double a = fmin(fmin(warp_max_step(sk, dsa, k, lane), warp_max_step(zk, dza, k, lane)), st);
         a = fmax(0.0, fmin(1.0, 0.99 * a));
+        __syncwarp();
         for (int j = lane; j < k; j += 32) { sk[j] += a * dsa[j]; zk[j] += a * dza[j]; }
         if (lane == 0) { sc[0] += a * sc[2]; sc[4] = a; }
         __syncwarp();
       }
       g.sync();
       const double a = sc[4];
-      for (int e = g.tid; e < n; e += g.T) yv[e] += a * rv[e];
+      for (int e = g.tid; e < n; e += T) yv[e] = fma(a, rv[e], yv[e]);
       g.sync();
     }
   } else {
@@ -550,22 +642,29 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
       if (g.tid == 0) zk[0] = 1.0;  // lam = [1]  (:166-168)
       g.sync();
     } else {
-      for (int j = g.tid; j < k; j += g.T) { zk[j] = 1.0 / k; ck[j] = rsu[permu[j]] + hk[j]; ek[j] = 1.0; }
+      for (int j = g.tid; j < k; j += T) { zk[j] = 1.0 / k; ck[j] = rsu[permu[j]] + hk[j]; ek[j] = 1.0; }
       g.sync();
       bool done = false;
       for (int it = 0; it < maxit && !done; ++it) {
         inner_its = it + 1;
         // column pass: a = G^T lam ; z = sigma(a) ; F = -c.lam + sum softplus(a)
         double fs = 0.0;
-        for (int e = g.tid; e < n; e += g.T) {
-          double a = 0.0;
-          for (int j = 0; j < k; ++j) a = fma((double)__ldg(rowp[j] + e), zk[j], a);
-          const double ze = 1.0 / (1.0 + exp(-a));
-          yv[e] = ze;
-          dv[e] = ze * (1.0 - ze);
-          fs += softplus_d(a);
+        for (int cb = 0; cb < n; cb += CH * T) {
+          double acc[CH];
+          col_dots<T>(rowp, k, n, cb, g.tid, zk, acc);
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const int e = cb + c * T + g.tid;
+            if (e < n) {
+              const double ze = 1.0 / (1.0 + exp(-acc[c]));
+              yv[e] = ze;
+              dv[e] = ze * (1.0 - ze);
+              fs += softplus_d(acc[c]);
+            }
+          }
         }
         fs = g.sum(fs);
+        if (WPS == 1) __syncwarp();
         // row pass: grad = -c + G z
         for (int j = g.warp; j < k; j += WPS) {
           const float* rj = rowp[j];
@@ -592,8 +691,6 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
           }
           const int p = bi;
           // change of variables, reduced gradient / Hessian, bound set
-          int nfree = 0;
-          double gn = 0.0;
           for (int j = lane; j < k; j += 32) {
             yk[j] = (j == p) ? 1.0 : zk[j];
             ek[j] = (j == p) ? 0.0 : 1.0;
@@ -601,7 +698,7 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
           __syncwarp();
           for (int j = lane; j < k; j += 32) g0[j] = gk[j] - ek[j] * gk[p];
           __syncwarp();
-          // free list in tk (as doubles holding indices) -- built serially by lane 0 (k <= 64)
+          // free list in tk (indices as doubles), built serially by lane 0 (k <= 64)
           if (lane == 0) {
             int nf = 0;
             for (int j = 0; j < k; ++j) {
@@ -611,7 +708,8 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
             isc[4] = nf;
           }
           __syncwarp();
-          nfree = isc[4];
+          const int nfree = isc[4];
+          double gn = 0.0;
           for (int a = lane; a < nfree; a += 32) { const double v = g0[(int)tk[a]]; gn = fma(v, v, gn); }
           gn = Grp<1>::wsum(gn);
           if (sqrt(gn) < 1e-10) {
@@ -627,11 +725,12 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
               rk[a] = -g0[i];
             }
             __syncwarp();
-            const bool ok = warp_cholesky(Lm, nfree, ld, lane, nullptr);
+            const bool ok = warp_cholesky(Lm, invd, nfree, ld, lane);
             if (!ok) {
               if (lane == 0) isc[5] = 2;  // solve failure (RL: break; dual: flagged)
             } else {
-              warp_chol_solve(Lm, nfree, ld, rk, lane);
+              double* const r1[1] = {rk};
+              warp_chol_solve<1>(Lm, invd, nfree, ld, r1, lane);
               for (int j = lane; j < k; j += 32) dk[j] = 0.0;
               __syncwarp();
               double dg = 0.0, dmax = 0.0;
@@ -680,10 +779,12 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
           if (lnk[p] >= 0.0) {
             if (cf.line_search) {
               double fs2 = 0.0;
-              for (int e = g.tid; e < n; e += g.T) {
-                double a = 0.0;
-                for (int j = 0; j < k; ++j) a = fma((double)__ldg(rowp[j] + e), lnk[j], a);
-                fs2 += softplus_d(a);
+              for (int cb = 0; cb < n; cb += CH * T) {
+                double acc[CH];
+                col_dots<T>(rowp, k, n, cb, g.tid, lnk, acc);
+#pragma unroll
+                for (int c = 0; c < CH; ++c)
+                  if (cb + c * T + g.tid < n) fs2 += softplus_d(acc[c]);
               }
               fs2 = g.sum(fs2);
               double cl = 0.0;
@@ -702,16 +803,20 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
           g.sync();
         }
         g.sync();
-        for (int j = g.tid; j < k; j += g.T) zk[j] = lnk[j];
+        for (int j = g.tid; j < k; j += T) zk[j] = lnk[j];
         g.sync();
         if (ret_now) done = true;
       }
     }
     // y = 1 / (1 + exp(G^T lam))   (:165 / :168)
-    for (int e = g.tid; e < n; e += g.T) {
-      double a = 0.0;
-      for (int j = 0; j < k; ++j) a = fma((double)__ldg(rowp[j] + e), zk[j], a);
-      yv[e] = 1.0 / (1.0 + exp(a));
+    for (int cb = 0; cb < n; cb += CH * T) {
+      double acc[CH];
+      col_dots<T>(rowp, k, n, cb, g.tid, zk, acc);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int e = cb + c * T + g.tid;
+        if (e < n) yv[e] = 1.0 / (1.0 + exp(acc[c]));
+      }
     }
     g.sync();
   }
@@ -719,7 +824,7 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
   // ---- commit: y, lambda, prune, bookkeeping -------------------------------------------------
   double maxdiff = 0.0, bad = 0.0;
   const bool rl = (cf.variant == ICNN_VARIANT_RL);
-  for (int e = g.tid; e < n; e += g.T) {
+  for (int e = g.tid; e < n; e += T) {
     double ye = yv[e];
     if (rl) ye = fmin(fmax(ye, 0.03), 0.97);  // RL/src/bundle_entropy.py:118,123
     if (!isfinite(ye)) bad = 1.0;
@@ -729,34 +834,29 @@ __global__ void __launch_bounds__(256) bundle_step_kernel(StepArgs A) {
   }
   if (rl) maxdiff = g.max(maxdiff);
   bad = g.max(bad);
-  if (g.warp == 0) {
-    const int lane = g.lane;
+  if (g.tid == 0) {
     // prune (keep lam > thr), rebuild perm: kept slots, then dropped, then the old free tail
-    if (lane == 0) {
-      int nk = 0;
-      int dropped[64];
-      int nd = 0;
-      int* pw = b.perm + (size_t)u * KS;
-      int oldp[64];
-      for (int j = 0; j < k; ++j) oldp[j] = pw[j];
-      for (int j = 0; j < k; ++j) {
-        const double lj = zk[j];
-        if (lj > cf.prune_thr) { pw[nk++] = oldp[j]; lamu[oldp[j]] = lj; }
-        else dropped[nd++] = oldp[j];
-      }
-      for (int j = 0; j < nd; ++j) pw[nk + j] = dropped[j];
-      b.count[u] = nk;
-      int fin = 0;
-      int stt = ICNN_ST_RUNNING;
-      if (fail) stt = ICNN_ST_SOLVE_FAIL;
-      if (bad > 0.0) { stt = ICNN_ST_NONFINITE; fin = 1; }
-      if (rl && maxdiff < 1e-6) { fin = 1; if (stt == ICNN_ST_RUNNING) stt = ICNN_ST_CONVERGED; }
-      b.status[u] = stt;
-      if (fin) b.finished[u] = 1;
-      else atomicAdd(&b.nactive[A.t + 1], 1);
-      if (b.newton_its) b.newton_its[u] += inner_its;
-      if (b.ksum) b.ksum[u] += k;
+    int nk = 0, nd = 0;
+    int dropped[64], oldp[64];
+    int* pw = b.perm + (size_t)u * KS;
+    for (int j = 0; j < k; ++j) oldp[j] = pw[j];
+    for (int j = 0; j < k; ++j) {
+      const double lj = zk[j];
+      if (lj > cf.prune_thr) { pw[nk++] = oldp[j]; lamu[oldp[j]] = lj; }
+      else dropped[nd++] = oldp[j];
     }
+    for (int j = 0; j < nd; ++j) pw[nk + j] = dropped[j];
+    b.count[u] = nk;
+    int fin = 0;
+    int stt = ICNN_ST_RUNNING;
+    if (fail) stt = ICNN_ST_SOLVE_FAIL;
+    if (bad > 0.0) { stt = ICNN_ST_NONFINITE; fin = 1; }
+    if (rl && maxdiff < 1e-6) { fin = 1; if (stt == ICNN_ST_RUNNING) stt = ICNN_ST_CONVERGED; }
+    b.status[u] = stt;
+    if (fin) b.finished[u] = 1;
+    else atomicAdd(&b.nactive[A.t + 1], 1);
+    if (b.newton_its) b.newton_its[u] += inner_its;
+    if (b.ksum) b.ksum[u] += k;
   }
 }
 
@@ -800,15 +900,14 @@ int bundle_step_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, in
   }
   if (b->KS > 64) { set_error("bundle_step: KS=%d > 64 unsupported", b->KS); return ICNN_E_UNSUPPORTED; }
   cudaError_t e;
-  if (wps == 1) {
-    e = cudaFuncSetAttribute(bundle_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
-    bundle_step_kernel<1><<<cdiv(b->B, 8), 256, smem, st>>>(a);
-  } else {
-    e = cudaFuncSetAttribute(bundle_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
-    bundle_step_kernel<8><<<b->B, 256, smem, st>>>(a);
-  }
+  // ICNN_K2_MINB=2 selects the 128-register build (2 CTAs/SM); default 3 CTAs/SM (80 registers)
+  static const int minb = [] { const char* v = getenv("ICNN_K2_MINB"); return (v && v[0] == '2') ? 2 : 3; }();
+  void (*kern)(StepArgs) = nullptr;
+  if (wps == 1) kern = (minb == 2) ? bundle_step_kernel<1, 2> : bundle_step_kernel<1, 3>;
+  else kern = (minb == 2) ? bundle_step_kernel<8, 2> : bundle_step_kernel<8, 3>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
+  kern<<<wps == 1 ? cdiv(b->B, 8) : b->B, 256, smem, st>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("bundle_step launch: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
   return ICNN_OK;

@@ -14,6 +14,10 @@
 // This FP32 kernel is the accuracy anchor for the tcgen05 path (picnn_tc.cu).
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
 namespace icnn {
 
 struct GemmArgs {
@@ -39,13 +43,36 @@ __device__ __forceinline__ float* g_row_ptr(const GemmArgs& a, int m) {
   return a.g + ((long long)m * a.KS + slot) * a.n;
 }
 
+// One output element of the fused epilogue (shared by the register and the split-K paths).
+template <int MODE>
+__device__ __forceinline__ void epilogue_elem(const GemmArgs& a, int m, int nn, float acc, float* grow) {
+  if (MODE == 0) {
+    const float v = acc + a.D[(long long)m * a.N + nn];
+    a.Z[(long long)m * a.N + nn] = v > 0.f ? v : a.alpha * v;
+  } else {
+    if (nn < a.N0) {
+      const long long idx = (long long)m * a.N0 + nn;
+      const float da = a.Zprev[idx] > 0.f ? 1.f : a.alpha;
+      a.dprev[idx] = da * a.Cz[idx] * acc;
+    } else {
+      const int e = nn - a.N0;
+      grow[e] = fmaf(a.g_scale * a.Cy[(long long)m * a.n + e], acc, grow[e]);
+    }
+  }
+}
+
 // MODE 0: forward (W is [K, N]);  MODE 1: backward (W is [N, K], K = K0, no second segment)
+// Split-K: gridDim.z = S CTAs of one thread-block cluster share an output tile; each reduces a
+// K-slice, the partial tiles are summed through distributed shared memory (rank r owns BM/S rows
+// of the tile for the reduction + epilogue).  S = 1 is the plain kernel.
 template <int MODE>
 __global__ void __launch_bounds__(256) gated_gemm_kernel(GemmArgs a) {
   if (a.skip_if_zero != nullptr && *a.skip_if_zero == 0) return;
-  __shared__ float As[2][BK][BM + PAD];
-  __shared__ float Bs[2][BK][BN + PAD];
+  __shared__ __align__(16) float smem_f[2 * BK * (BM + PAD) + 2 * BK * (BN + PAD)];
+  float (*As)[BK][BM + PAD] = reinterpret_cast<float (*)[BK][BM + PAD]>(smem_f);
+  float (*Bs)[BK][BN + PAD] = reinterpret_cast<float (*)[BK][BN + PAD]>(smem_f + 2 * BK * (BM + PAD));
   const int t = threadIdx.x;
+  const int S = gridDim.z;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int K = a.K0 + a.K1;
   const int ty = t / 16, tx = t % 16;
@@ -108,13 +135,14 @@ __global__ void __launch_bounds__(256) gated_gemm_kernel(GemmArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  const int nk = (K + BK - 1) / BK;
-  load_tiles(0);
-  store_tiles(0);
+  const int nk_all = (K + BK - 1) / BK;
+  const int kt0 = (int)(((long long)nk_all * blockIdx.z) / S);
+  const int nk = (int)(((long long)nk_all * (blockIdx.z + 1)) / S) - kt0;
+  if (nk > 0) { load_tiles(kt0 * BK); store_tiles(0); }
   __syncthreads();
   for (int kt = 0; kt < nk; ++kt) {
     const int buf = kt & 1;
-    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+    if (kt + 1 < nk) load_tiles((kt0 + kt + 1) * BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       const float4 av = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
@@ -130,30 +158,45 @@ __global__ void __launch_bounds__(256) gated_gemm_kernel(GemmArgs a) {
     __syncthreads();
   }
 
+  if (S == 1) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
-    if (m >= a.M) continue;
-    float* grow = (MODE == 1) ? g_row_ptr(a, m) : nullptr;
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      if (m >= a.M) continue;
+      float* grow = (MODE == 1) ? g_row_ptr(a, m) : nullptr;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int nn = n0 + tx * 4 + j;
-      if (nn >= a.N) continue;
-      if (MODE == 0) {
-        const float v = acc[i][j] + a.D[(long long)m * a.N + nn];
-        a.Z[(long long)m * a.N + nn] = v > 0.f ? v : a.alpha * v;
-      } else {
-        if (nn < a.N0) {
-          const long long idx = (long long)m * a.N0 + nn;
-          const float da = a.Zprev[idx] > 0.f ? 1.f : a.alpha;
-          a.dprev[idx] = da * a.Cz[idx] * acc[i][j];
-        } else {
-          const int e = nn - a.N0;
-          grow[e] = fmaf(a.g_scale * a.Cy[(long long)m * a.n + e], acc[i][j], grow[e]);
-        }
+      for (int j = 0; j < 4; ++j) {
+        const int nn = n0 + tx * 4 + j;
+        if (nn < a.N) epilogue_elem<MODE>(a, m, nn, acc[i][j], grow);
       }
     }
+    return;
   }
+  // ---- split-K: partial tile -> own shared memory -> DSMEM reduction ----
+  cg::cluster_group cluster = cg::this_cluster();
+  float (*Ps)[BN + 1] = reinterpret_cast<float (*)[BN + 1]>(smem_f);   // [BM][BN+1] floats fit
+  static_assert(BM * (BN + 1) <= 2 * BK * (BM + PAD) + 2 * BK * (BN + PAD), "partial tile must fit");
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Ps[ty * 4 + i][tx * 4 + j] = acc[i][j];
+  cluster.sync();
+  const int rank = (int)cluster.block_rank();
+  const int r_lo = (BM * rank) / S, r_hi = (BM * (rank + 1)) / S;
+  for (int idx = t; idx < (r_hi - r_lo) * BN; idx += 256) {
+    const int rr = r_lo + idx / BN, cc = idx % BN;
+    float v = 0.f;
+    for (int q = 0; q < S; ++q) {
+      const float* rp = cluster.map_shared_rank(&Ps[rr][cc], q);
+      v += *rp;
+    }
+    const int m = m0 + rr, nn = n0 + cc;
+    if (m < a.M && nn < a.N) {
+      float* grow = (MODE == 1 && nn >= a.N0) ? g_row_ptr(a, m) : nullptr;
+      epilogue_elem<MODE>(a, m, nn, v, grow);
+    }
+  }
+  cluster.sync();   // keep every CTA's partial tile alive until all ranks have read it
 }
 
 struct OutArgs {
@@ -213,6 +256,26 @@ __global__ void gd_update_kernel(float* y, float* v, const float* g, long long N
   v[i] = vn;
 }
 
+// Launch with a (1,1,S) thread-block cluster; S chosen so that the grid covers the chip at least
+// ~2x while every CTA keeps >= 4 k-tiles.
+template <int MODE>
+static cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t st) {
+  const int gx = cdiv(a.N, BN), gy = cdiv(a.M, BM);
+  const int nk = cdiv(a.K0 + a.K1, BK);
+  int S = 1;
+  while (S < 8 && gx * gy * S < 296 && nk / (S * 2) >= 4) S *= 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, gy, S);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gated_gemm_kernel<MODE>, a);
+}
+
 // workspace layout: Z_0..Z_{L-1} [B, s_i], then two delta buffers [B, smax]
 static size_t ws_floats(const icnn_picnn* h, int B, size_t* zoff, size_t* doff) {
   size_t off = 0;
@@ -246,8 +309,8 @@ int picnn_fg_simt(const icnn_picnn* h, const icnn_gates* gt, const float* y32, f
     a.A1 = y32; a.G1 = gt->cy[i]; a.lda1 = n; a.a1_scale = gt->in_scale; a.a1_shift = gt->in_shift;
     a.W = h->Wcat[i]; a.ldw = a.N;
     a.D = gt->d[i]; a.Z = Z[i]; a.alpha = h->alpha; a.skip_if_zero = skip;
-    dim3 grid(cdiv(a.N, BN), cdiv(B, BM));
-    gated_gemm_kernel<0><<<grid, 256, 0, st>>>(a);
+    cudaError_t le = launch_gemm<0>(a, st);
+    if (le != cudaSuccess) { set_error("gated_gemm<0> launch: %s", cudaGetErrorString(le)); return ICNN_E_CUDA; }
   }
   {
     OutArgs o{};
@@ -266,8 +329,8 @@ int picnn_fg_simt(const icnn_picnn* h, const icnn_gates* gt, const float* y32, f
     a.Zprev = i ? Z[i - 1] : nullptr; a.Cz = i ? gt->cz[i] : nullptr; a.dprev = dl[cur ^ 1];
     a.Cy = gt->cy[i]; a.g = g; a.g_row_stride = g_row_stride; a.perm = perm; a.count = count; a.KS = KS;
     a.n = n; a.g_scale = gt->g_scale; a.skip_if_zero = skip;
-    dim3 grid(cdiv(a.N, BN), cdiv(B, BM));
-    gated_gemm_kernel<1><<<grid, 256, 0, st>>>(a);
+    cudaError_t le = launch_gemm<1>(a, st);
+    if (le != cudaSuccess) { set_error("gated_gemm<1> launch: %s", cudaGetErrorString(le)); return ICNN_E_CUDA; }
     cur ^= 1;
   }
   cudaError_t e = cudaGetLastError();
