@@ -188,37 +188,48 @@ __device__ __forceinline__ double softplus_d(double x) {  // lib/bundle_entropy_
 
 // ---- G passes -----------------------------------------------------------------------------
 
-constexpr int CH = 8;  // columns per thread per chunk in a column pass
-
-// column pass core: acc[c] = sum_j G_j[e_c] * w[j] for this thread's CH columns
-// e_c = base + c*T + tid.  The row loop is outermost so w[j] and the row pointer are read from
-// shared memory once per CH global loads.
-template <int T>
-__device__ __forceinline__ void col_dots(const float* const* rowp, int k, int n, int base, int tid,
-                                         const double* w, double (&acc)[CH]) {
+// column pass core: acc[c] = sum_j G_j[e_c] * w[j] for this thread's CHN columns
+// e_c = cb + c*T + tid.  The row loop is outermost so w[j] and the row pointer are read from
+// shared memory once per CHN global loads.  PRED: guard e_c < n (ragged tail only).
+template <int T, int CHN, bool PRED>
+__device__ __forceinline__ void col_dots(const float* const* rowp, int k, int n, int cb, int tid,
+                                         const double* w, double (&acc)[CHN]) {
 #pragma unroll
-  for (int c = 0; c < CH; ++c) acc[c] = 0.0;
-  if (base + CH * T <= n) {
-    for (int j = 0; j < k; ++j) {
-      const float* p = rowp[j] + base + tid;
-      const double wj = w[j];
-      float v[CH];
+  for (int c = 0; c < CHN; ++c) acc[c] = 0.0;
+  for (int j = 0; j < k; ++j) {
+    const float* p = rowp[j] + cb + tid;
+    const double wj = w[j];
+    float v[CHN];
 #pragma unroll
-      for (int c = 0; c < CH; ++c) v[c] = __ldg(p + c * T);
+    for (int c = 0; c < CHN; ++c) v[c] = (!PRED || cb + c * T + tid < n) ? __ldg(p + c * T) : 0.f;
 #pragma unroll
-      for (int c = 0; c < CH; ++c) acc[c] = fma((double)v[c], wj, acc[c]);
-    }
-  } else {
-    for (int j = 0; j < k; ++j) {
-      const float* p = rowp[j] + base + tid;
-      const double wj = w[j];
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const float v = (base + c * T + tid < n) ? __ldg(p + c * T) : 0.f;
-        acc[c] = fma((double)v, wj, acc[c]);
-      }
-    }
+    for (int c = 0; c < CHN; ++c) acc[c] = fma((double)v[c], wj, acc[c]);
   }
+}
+
+template <int T, int CHN, bool PRED, class F>
+__device__ __forceinline__ void col_chunk(const float* const* rowp, int k, int n, int cb, int tid,
+                                          const double* w, F&& f) {
+  double acc[CHN];
+  col_dots<T, CHN, PRED>(rowp, k, n, cb, tid, w, acc);
+#pragma unroll
+  for (int c = 0; c < CHN; ++c) {
+    const int e = cb + c * T + tid;
+    if (!PRED || e < n) f(e, acc[c]);
+  }
+}
+
+// column pass: for every column e, f(e, sum_j G_j[e] w[j]).  8 columns per thread per chunk while
+// they last, then 4 / 2 / 1, then one predicated chunk for the ragged tail.
+template <int T, class F>
+__device__ __forceinline__ void col_pass(const float* const* rowp, int k, int n, int tid,
+                                         const double* w, F&& f) {
+  int cb = 0;
+  for (; cb + 8 * T <= n; cb += 8 * T) col_chunk<T, 8, false>(rowp, k, n, cb, tid, w, f);
+  if (cb + 4 * T <= n) { col_chunk<T, 4, false>(rowp, k, n, cb, tid, w, f); cb += 4 * T; }
+  if (cb + 2 * T <= n) { col_chunk<T, 2, false>(rowp, k, n, cb, tid, w, f); cb += 2 * T; }
+  if (cb + T <= n) { col_chunk<T, 1, false>(rowp, k, n, cb, tid, w, f); cb += T; }
+  if (cb < n) col_chunk<T, 1, true>(rowp, k, n, cb, tid, w, f);
 }
 
 // gram pass: M[i][j] = sum_e w[e] G_i[e] G_j[e] (symmetric fill), w == nullptr -> 1
@@ -403,19 +414,11 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
         for (int rep = 0; rep < 2; ++rep) {
           // residual res = (rep ? res : gnew) - sum_j c_j G_j
           double p = 0.0;
-          for (int cb = 0; cb < n; cb += CH * T) {
-            double acc[CH];
-            col_dots<T>(rowp, k0, n, cb, g.tid, rk, acc);
-#pragma unroll
-            for (int c = 0; c < CH; ++c) {
-              const int e = cb + c * T + g.tid;
-              if (e < n) {
-                const double r = (rep ? rv[e] : (double)gnew[e]) - acc[c];
-                rv[e] = r;
-                p = fma(r, r, p);
-              }
-            }
-          }
+          col_pass<T>(rowp, k0, n, g.tid, rk, [&](int e, double a) {
+            const double r = (rep ? rv[e] : (double)gnew[e]) - a;
+            rv[e] = r;
+            p = fma(r, r, p);
+          });
           p = g.sum(p);
           if (p <= thr2) { dependent = true; break; }
           // clearly independent (relative distance > 1e-4), or already refined once
@@ -463,21 +466,13 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
     for (int it = 0; it < maxit; ++it) {
       // column pass: ry = log y - log(1-y) + G^T z ; D = y(1-y) = 1/(1/y + 1/(1-y))
       double pr = 0.0;
-      for (int cb = 0; cb < n; cb += CH * T) {
-        double acc[CH];
-        col_dots<T>(rowp, k, n, cb, g.tid, zk, acc);
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const int e = cb + c * T + g.tid;
-          if (e < n) {
-            const double ye = yv[e];
-            const double r = log(ye) - log(1.0 - ye) + acc[c];
-            rv[e] = r;
-            dv[e] = ye * (1.0 - ye);
-            pr = fma(r, r, pr);
-          }
-        }
-      }
+      col_pass<T>(rowp, k, n, g.tid, zk, [&](int e, double a) {
+        const double ye = yv[e];
+        const double r = log(ye) - log(1.0 - ye) + a;
+        rv[e] = r;
+        dv[e] = ye * (1.0 - ye);
+        pr = fma(r, r, pr);
+      });
       pr = g.sum(pr);   // (contains the barrier that publishes rv / dv)
       if (WPS == 1) __syncwarp();
       // row pass: rd = G y + h - t + s ; q = G D ry
@@ -542,21 +537,13 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
       inner_its = it + 1;
       // column pass: dy_aff = -D (ry + G^T dz_aff) ; get_step(y, dy) and get_step(1-y, -dy)
       double st = 1e300, st2 = 1e300;
-      for (int cb = 0; cb < n; cb += CH * T) {
-        double acc[CH];
-        col_dots<T>(rowp, k, n, cb, g.tid, dza, acc);
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const int e = cb + c * T + g.tid;
-          if (e < n) {
-            const double dy = -dv[e] * (rv[e] + acc[c]);
-            rv[e] = dy;  // rv now holds dy_aff
-            const double ye = yv[e];
-            if (dy < 0.0) st = fmin(st, -ye / dy);
-            if (dy > 0.0) st2 = fmin(st2, (1.0 - ye) / dy);
-          }
-        }
-      }
+      col_pass<T>(rowp, k, n, g.tid, dza, [&](int e, double a) {
+        const double dy = -dv[e] * (rv[e] + a);
+        rv[e] = dy;  // rv now holds dy_aff
+        const double ye = yv[e];
+        if (dy < 0.0) st = fmin(st, -ye / dy);
+        if (dy > 0.0) st2 = fmin(st2, (1.0 - ye) / dy);
+      });
       st = g.min(st);
       st2 = g.min(st2);
       st = fmin(st > 1e299 ? 1.0 : st, st2 > 1e299 ? 1.0 : st2);
@@ -600,21 +587,13 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
       g.sync();
       // column pass: dy = dy_aff - D G^T dz_cor ; step bounds
       st = 1e300; st2 = 1e300;
-      for (int cb = 0; cb < n; cb += CH * T) {
-        double acc[CH];
-        col_dots<T>(rowp, k, n, cb, g.tid, dzc, acc);
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const int e = cb + c * T + g.tid;
-          if (e < n) {
-            const double dy = rv[e] - dv[e] * acc[c];
-            rv[e] = dy;
-            const double ye = yv[e];
-            if (dy < 0.0) st = fmin(st, -ye / dy);
-            if (dy > 0.0) st2 = fmin(st2, (1.0 - ye) / dy);
-          }
-        }
-      }
+      col_pass<T>(rowp, k, n, g.tid, dzc, [&](int e, double a) {
+        const double dy = rv[e] - dv[e] * a;
+        rv[e] = dy;
+        const double ye = yv[e];
+        if (dy < 0.0) st = fmin(st, -ye / dy);
+        if (dy > 0.0) st2 = fmin(st2, (1.0 - ye) / dy);
+      });
       st = g.min(st);
       st2 = g.min(st2);
       st = fmin(st > 1e299 ? 1.0 : st, st2 > 1e299 ? 1.0 : st2);
@@ -649,20 +628,12 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
         inner_its = it + 1;
         // column pass: a = G^T lam ; z = sigma(a) ; F = -c.lam + sum softplus(a)
         double fs = 0.0;
-        for (int cb = 0; cb < n; cb += CH * T) {
-          double acc[CH];
-          col_dots<T>(rowp, k, n, cb, g.tid, zk, acc);
-#pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            const int e = cb + c * T + g.tid;
-            if (e < n) {
-              const double ze = 1.0 / (1.0 + exp(-acc[c]));
-              yv[e] = ze;
-              dv[e] = ze * (1.0 - ze);
-              fs += softplus_d(acc[c]);
-            }
-          }
-        }
+        col_pass<T>(rowp, k, n, g.tid, zk, [&](int e, double a) {
+          const double ze = 1.0 / (1.0 + exp(-a));
+          yv[e] = ze;
+          dv[e] = ze * (1.0 - ze);
+          fs += softplus_d(a);
+        });
         fs = g.sum(fs);
         if (WPS == 1) __syncwarp();
         // row pass: grad = -c + G z
@@ -779,13 +750,7 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
           if (lnk[p] >= 0.0) {
             if (cf.line_search) {
               double fs2 = 0.0;
-              for (int cb = 0; cb < n; cb += CH * T) {
-                double acc[CH];
-                col_dots<T>(rowp, k, n, cb, g.tid, lnk, acc);
-#pragma unroll
-                for (int c = 0; c < CH; ++c)
-                  if (cb + c * T + g.tid < n) fs2 += softplus_d(acc[c]);
-              }
+              col_pass<T>(rowp, k, n, g.tid, lnk, [&](int e, double a) { fs2 += softplus_d(a); });
               fs2 = g.sum(fs2);
               double cl = 0.0;
               for (int j = 0; j < k; ++j) cl = fma(ck[j], lnk[j], cl);
@@ -809,15 +774,7 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
       }
     }
     // y = 1 / (1 + exp(G^T lam))   (:165 / :168)
-    for (int cb = 0; cb < n; cb += CH * T) {
-      double acc[CH];
-      col_dots<T>(rowp, k, n, cb, g.tid, zk, acc);
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const int e = cb + c * T + g.tid;
-        if (e < n) yv[e] = 1.0 / (1.0 + exp(acc[c]));
-      }
-    }
+    col_pass<T>(rowp, k, n, g.tid, zk, [&](int e, double a) { yv[e] = 1.0 / (1.0 + exp(a)); });
     g.sync();
   }
 
@@ -885,7 +842,13 @@ __global__ void put_fg_kernel(icnn_bundle_bufs b, const float* f, const float* g
   if (threadIdx.x == 0) b.f[u] = f[u];
 }
 
-static int pick_wps(int n) { return n <= 128 ? 1 : 8; }
+// warps per sample: enough columns per thread to amortise the per-row shared-memory reads,
+// few enough warps that the warp-0 dense algebra does not idle most of the group
+static int pick_wps(int n) {
+  const char* v = getenv("ICNN_K2_WPS");
+  if (v) { const int w = atoi(v); if (w == 1 || w == 2 || w == 4 || w == 8) return w; }
+  return n <= 128 ? 1 : (n <= 512 ? 2 : (n <= 1024 ? 4 : 8));
+}
 
 int bundle_step_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int t, cudaStream_t st) {
   StepArgs a;
@@ -904,10 +867,12 @@ int bundle_step_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, in
   static const int minb = [] { const char* v = getenv("ICNN_K2_MINB"); return (v && v[0] == '2') ? 2 : 3; }();
   void (*kern)(StepArgs) = nullptr;
   if (wps == 1) kern = (minb == 2) ? bundle_step_kernel<1, 2> : bundle_step_kernel<1, 3>;
+  else if (wps == 2) kern = (minb == 2) ? bundle_step_kernel<2, 2> : bundle_step_kernel<2, 3>;
+  else if (wps == 4) kern = (minb == 2) ? bundle_step_kernel<4, 2> : bundle_step_kernel<4, 3>;
   else kern = (minb == 2) ? bundle_step_kernel<8, 2> : bundle_step_kernel<8, 3>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
-  kern<<<wps == 1 ? cdiv(b->B, 8) : b->B, 256, smem, st>>>(a);
+  kern<<<cdiv(b->B, 8 / wps), 256, smem, st>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("bundle_step launch: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
   return ICNN_OK;
