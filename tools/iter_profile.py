@@ -30,13 +30,13 @@ for rep in range(2):
         _capi.check(_capi.lib.icnn_picnn_fg(net._h, C.byref(fg.c_gates), st.y32.data_ptr(), st.f.data_ptr(), st.G.data_ptr(), 0,
                                             st.perm.data_ptr(), st.count.data_ptr(), KS, fg.ws.data_ptr(), None, stream))
         e1.record()
-        its0 = st.newton_its.sum().item() if rep else 0
         _capi.check(_capi.lib.icnn_bundle_step(C.byref(ccfg), C.byref(st.c), t, stream))
         e2.record()
         evs.append((e0, e1, e2))
         if rep:
-            cnt = st.count.cpu().numpy(); fin = st.finished.cpu().numpy()
-            stats.append((cnt.mean(), cnt.max(), int((fin == 0).sum()), (st.newton_its.sum().item() - its0)))
+            torch.cuda.synchronize()
+            cnt = st.count.cpu().numpy(); fin = st.finished.cpu().numpy(); ni = int(st.newton_its.cpu().numpy().sum())
+            stats.append((cnt.mean(), cnt.max(), int((fin == 0).sum()), ni - (stats[-1][4] if stats else 0), ni))
     torch.cuda.synchronize()
 print("%s B=%d n=%d nIter=%d solver=%s WPS=%s MINB=%s" % (name, B, n, nIter, solver, os.environ.get("ICNN_K2_WPS", "auto"), os.environ.get("ICNN_K2_MINB", "3")))
 k1 = [a.elapsed_time(b) for a, b, _ in evs]; k2 = [b.elapsed_time(c) for _, b, c in evs]
