@@ -137,8 +137,9 @@ def test_k2_against_reference_golden(case, maxtol, medtol, golden_dir):
     else:
         assert np.mean(d < 1e-4) >= 0.75, np.mean(d < 1e-4)
     assert np.median(d) < medtol, np.median(d)
-    agree = np.mean(lens(r[1]) == gold["counts"])
-    assert agree >= (0.5 if nIter > 10 else 0.8), agree
+    if maxtol != "long":      # active-set sizes only compare before the trajectories decorrelate
+        agree = np.mean(lens(r[1]) == gold["counts"])
+        assert agree >= (0.5 if nIter > 10 else 0.8), agree
 
 
 FUSED = [("C1", 64, 5, 1e-4), ("C4", 512, 5, 1e-4), ("T", 48, 10, 1e-4), ("C3", 96, 10, None), ("C2", 6, 30, None)]
