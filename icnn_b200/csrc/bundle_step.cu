@@ -232,14 +232,21 @@ __device__ __forceinline__ void col_pass(const float* const* rowp, int k, int n,
   if (cb < n) col_chunk<T, 1, true>(rowp, k, n, cb, tid, w, f);
 }
 
-// gram pass: M[i][j] = sum_e w[e] G_i[e] G_j[e] (symmetric fill), w == nullptr -> 1
+// FP64 tensor-core MMA, D(8x8) += A(8x4) * B(4x8).  Fragments (PTX ISA, m8n8k4 .f64):
+// A: lane holds A[lane/4][lane%4];  B: lane holds B[lane%4][lane/4];  C/D: lane holds
+// C[lane/4][2*(lane%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// gram pass (fallback, any n): warp owns 4x4 blocks of M = G diag(w) G^T, lanes stride columns.
 template <int WPS>
-__device__ inline void gram_pass(const Grp<WPS>& g, const float* const* rowp, int k, int n,
-                                 const double* w, double* M, int ld) {
+__device__ inline void gram_pass_simt(const Grp<WPS>& g, const float* const* rowp, int k, int n,
+                                      const double* w, double* M, int ld) {
   const int kb = (k + 3) >> 2;
   const int nblk = kb * (kb + 1) / 2;
   for (int blk = g.warp; blk < nblk; blk += WPS) {
-    // unrank blk -> (bi <= bj)
     int bi = 0, rem = blk;
     while (rem >= kb - bi) { rem -= kb - bi; ++bi; }
     const int bj = bi + rem;
@@ -256,7 +263,7 @@ __device__ inline void gram_pass(const Grp<WPS>& g, const float* const* rowp, in
 #pragma unroll
       for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
     for (int e = g.lane; e < n; e += 32) {
-      const double we = w ? w[e] : 1.0;
+      const double we = w[e];
       double vi[4], vj[4];
 #pragma unroll
       for (int a = 0; a < 4; ++a) { vi[a] = (double)__ldg(ri[a] + e) * we; vj[a] = (double)__ldg(rj[a] + e); }
@@ -276,6 +283,95 @@ __device__ inline void gram_pass(const Grp<WPS>& g, const float* const* rowp, in
   }
 }
 
+// gram pass on the FP64 tensor cores (n % 4 == 0): every warp sweeps its own 16-column groups
+// for ALL 8x8 tiles of the upper triangle (each row is read exactly once per pass), one
+// 128-bit load per lane per row block -- lane (r, q) = (lane/4, lane%4) gets columns 4q..4q+3
+// of row 8*rb + r, which are its A/B fragment elements for four consecutive k-steps (the four
+// columns of a k-step may be any four, as long as A, B and w agree).  Warp partials are then
+// added into M in warp order (deterministic).
+template <int WPS, int RB>
+__device__ inline void gram_sweep_dmma(const Grp<WPS>& g, const float* const* rowp, int k, int n,
+                                       const double* w, double* M, int ld) {
+  constexpr int NT = RB * (RB + 1) / 2;
+  double acc[NT][2];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
+  const int r = g.lane >> 2, q = g.lane & 3;
+  const float* rp[RB];
+  bool rv_[RB];
+#pragma unroll
+  for (int b = 0; b < RB; ++b) {
+    const int row = b * 8 + r;
+    rv_[b] = row < k;
+    rp[b] = rowp[rv_[b] ? row : k - 1] + 4 * q;
+  }
+  const int ngrp = (n + 15) >> 4;
+  for (int gi = g.warp; gi < ngrp; gi += WPS) {
+    const int col = gi * 16 + 4 * q;
+    const bool cv = col < n;  // n % 4 == 0: the whole float4 is in or out
+    float4 v[RB];
+#pragma unroll
+    for (int b = 0; b < RB; ++b)
+      v[b] = (cv && rv_[b]) ? __ldg(reinterpret_cast<const float4*>(rp[b] + gi * 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    double wv[4];
+    if (cv) {
+      const double2 w01 = *reinterpret_cast<const double2*>(w + col);
+      const double2 w23 = *reinterpret_cast<const double2*>(w + col + 2);
+      wv[0] = w01.x; wv[1] = w01.y; wv[2] = w23.x; wv[3] = w23.y;
+    } else {
+      wv[0] = wv[1] = wv[2] = wv[3] = 0.0;
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      double bf[RB], af[RB];
+#pragma unroll
+      for (int b = 0; b < RB; ++b) {
+        const float f = (s == 0) ? v[b].x : (s == 1) ? v[b].y : (s == 2) ? v[b].z : v[b].w;
+        bf[b] = (double)f;
+        af[b] = bf[b] * wv[s];
+      }
+      int t = 0;
+#pragma unroll
+      for (int bi = 0; bi < RB; ++bi)
+#pragma unroll
+        for (int bj = bi; bj < RB; ++bj) { dmma884(acc[t][0], acc[t][1], af[bi], bf[bj]); ++t; }
+    }
+  }
+  // ordered accumulation of the warp partials into M (symmetric fill)
+  for (int wv_i = 0; wv_i < WPS; ++wv_i) {
+    if (g.warp == wv_i) {
+      int t = 0;
+#pragma unroll
+      for (int bi = 0; bi < RB; ++bi)
+#pragma unroll
+        for (int bj = bi; bj < RB; ++bj) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int i = bi * 8 + r, j = bj * 8 + 2 * q + h;
+            if (i < k && j < k && (bi != bj || j >= i)) {
+              const double val = (wv_i == 0 ? 0.0 : M[i * ld + j]) + acc[t][h];
+              M[i * ld + j] = val;
+              M[j * ld + i] = val;
+            }
+          }
+          ++t;
+        }
+    }
+    g.sync();
+  }
+}
+
+template <int WPS>
+__device__ inline void gram_pass(const Grp<WPS>& g, const float* const* rowp, int k, int n,
+                                 const double* w, double* M, int ld) {
+  if ((n & 3) != 0 || k > 32) { gram_pass_simt<WPS>(g, rowp, k, n, w, M, ld); g.sync(); return; }
+  const int rb = (k + 7) >> 3;
+  if (rb == 1) gram_sweep_dmma<WPS, 1>(g, rowp, k, n, w, M, ld);
+  else if (rb == 2) gram_sweep_dmma<WPS, 2>(g, rowp, k, n, w, M, ld);
+  else if (rb == 3) gram_sweep_dmma<WPS, 3>(g, rowp, k, n, w, M, ld);
+  else gram_sweep_dmma<WPS, 4>(g, rowp, k, n, w, M, ld);
+}
+
 // ---- the step kernel ----------------------------------------------------------------------
 
 template <int WPS, int MINB>
@@ -283,7 +379,7 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
   const icnn_bundle_bufs& b = A.b;
   const icnn_bundle_cfg& cf = A.c;
   if (b.nactive[A.t] == 0) return;
-  extern __shared__ double smem_d[];
+  extern __shared__ __align__(16) double smem_d[];
   constexpr int GPB = 8 / WPS;  // groups per block
   constexpr int T = WPS * 32;
   Grp<WPS> g;
