@@ -196,6 +196,8 @@ __device__ __forceinline__ void col_dots(const float* const* rowp, int k, int n,
                                          const double* w, double (&acc)[CHN]) {
 #pragma unroll
   for (int c = 0; c < CHN; ++c) acc[c] = 0.0;
+  // several rows in flight per thread: the row loads are L2-latency bound
+#pragma unroll (CHN >= 8 ? 2 : 4)
   for (int j = 0; j < k; ++j) {
     const float* p = rowp[j] + cb + tid;
     const double wj = w[j];

@@ -14,7 +14,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int picnn_fg_simt(const icnn_picnn* h, const icnn_gates* gt, const float* y32, float* f, float* g,
+int picnn_fg_dispatch(const icnn_picnn* h, const icnn_gates* gt, const float* y32, float* f, float* g,
                   long long g_row_stride, const int* perm, const int* count, int KS, void* workspace,
                   const int* skip, cudaStream_t st);
 int bundle_step_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int t, cudaStream_t st);
@@ -43,7 +43,7 @@ extern "C" int icnn_solve_batch_fused(const icnn_picnn_t* h, const icnn_gates* g
   int rc = icnn_bundle_init(b, cfg->nIter, stream);
   if (rc) return rc;
   for (int t = 0; t < cfg->nIter; ++t) {
-    rc = picnn_fg_simt(h, gates, b->y32, b->f, b->G, 0, b->perm, b->count, b->KS, workspace,
+    rc = picnn_fg_dispatch(h, gates, b->y32, b->f, b->G, 0, b->perm, b->count, b->KS, workspace,
                        b->nactive + t, st);
     if (rc) return rc;
     rc = icnn_bundle_step(cfg, b, t, stream);

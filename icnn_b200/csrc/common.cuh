@@ -42,6 +42,11 @@ struct icnn_picnn {
   float alpha;
   // Wcat[i], i = 0..L : [(s_{i-1} + n), s_i] row-major = [Wz_i ; Wy_i]  (s_{-1} = 0, s_L = 1)
   float* Wcat[ICNN_MAX_LAYERS + 1];
+  // tensor-core path (picnn_tc.cu), hidden layers only: TF32 hi/lo splits of Wcat_i as stored
+  // ([K_f, s_i]: K-major B operand of the backward GEMM) and transposed ([s_i, K_f]: forward)
+  float* Wb_hi[ICNN_MAX_LAYERS]; float* Wb_lo[ICNN_MAX_LAYERS];
+  float* Wf_hi[ICNN_MAX_LAYERS]; float* Wf_lo[ICNN_MAX_LAYERS];
+  bool use_tc;
   int width(int i) const { return i < L ? hidden[i] : 1; }
   int prev(int i) const { return i == 0 ? 0 : hidden[i - 1]; }
 };

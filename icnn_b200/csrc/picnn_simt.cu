@@ -16,6 +16,8 @@
 
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 namespace cg = cooperative_groups;
 
 namespace icnn {
@@ -207,6 +209,7 @@ struct OutArgs {
   const float* w;                        // [S + n]  = [wz_L ; wy_L]
   float in_scale, in_shift, g_scale, alpha;
   float* f; float* delta;                // [M], [M, S]
+  float* delta_hi; float* delta_lo;      // optional TF32 hi/lo split of delta (tensor-core path)
   float* g; long long g_row_stride; const int* perm; const int* count; int KS;
   const int* skip_if_zero;
 };
@@ -223,7 +226,13 @@ __global__ void __launch_bounds__(256) out_layer_kernel(OutArgs a) {
     const long long idx = (long long)m * a.S + j;
     const float z = a.Z[idx], c = a.Cz[idx] * a.w[j];
     acc = fmaf(z, c, acc);
-    a.delta[idx] = (z > 0.f ? 1.f : a.alpha) * c;
+    const float dl = (z > 0.f ? 1.f : a.alpha) * c;
+    if (a.delta) a.delta[idx] = dl;
+    if (a.delta_hi) {
+      const float h = __uint_as_float(__float_as_uint(dl) & 0xFFFFE000u);
+      a.delta_hi[idx] = h;
+      a.delta_lo[idx] = dl - h;
+    }
   }
   float* grow;
   if (a.perm == nullptr) grow = a.g + (long long)m * a.g_row_stride;
@@ -277,7 +286,7 @@ static cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t st) {
 }
 
 // workspace layout: Z_0..Z_{L-1} [B, s_i], then two delta buffers [B, smax]
-static size_t ws_floats(const icnn_picnn* h, int B, size_t* zoff, size_t* doff) {
+size_t picnn_simt_ws_floats(const icnn_picnn* h, int B, size_t* zoff, size_t* doff) {
   size_t off = 0;
   int smax = 0;
   for (int i = 0; i < h->L; ++i) {
@@ -291,12 +300,32 @@ static size_t ws_floats(const icnn_picnn* h, int B, size_t* zoff, size_t* doff) 
   return off;
 }
 
+void out_layer_launch(const icnn_picnn* h, const icnn_gates* gt, const float* Zlast, const float* y32, float* f,
+                      float* delta, float* delta_hi, float* delta_lo, float* g, long long g_row_stride,
+                      const int* perm, const int* count, int KS, const int* skip, cudaStream_t st) {
+  const int B = gt->B, L = h->L;
+  OutArgs o{};
+  o.M = B; o.S = h->hidden[L - 1]; o.n = h->n; o.Z = Zlast; o.Cz = gt->cz[L]; o.y = y32; o.Cy = gt->cy[L];
+  o.D = gt->d[L]; o.w = h->Wcat[L]; o.in_scale = gt->in_scale; o.in_shift = gt->in_shift;
+  o.g_scale = gt->g_scale; o.alpha = h->alpha; o.f = f; o.delta = delta; o.delta_hi = delta_hi; o.delta_lo = delta_lo;
+  o.g = g; o.g_row_stride = g_row_stride; o.perm = perm; o.count = count; o.KS = KS; o.skip_if_zero = skip;
+  out_layer_kernel<<<cdiv(B * 32, 256), 256, 0, st>>>(o);
+}
+
+bool picnn_tc_supported(const icnn_picnn* h);
+int picnn_tc_prepare_weights(icnn_picnn* h, cudaStream_t st);
+void picnn_tc_free_weights(icnn_picnn* h);
+size_t picnn_tc_ws_floats(const icnn_picnn* h, int B, size_t* aoff, size_t* doff);
+int picnn_fg_tc(const icnn_picnn* h, const icnn_gates* gt, const float* y32, float* f, float* g,
+                long long g_row_stride, const int* perm, const int* count, int KS, void* workspace,
+                const int* skip, cudaStream_t st);
+
 int picnn_fg_simt(const icnn_picnn* h, const icnn_gates* gt, const float* y32, float* f, float* g,
                   long long g_row_stride, const int* perm, const int* count, int KS, void* workspace,
                   const int* skip, cudaStream_t st) {
   const int B = gt->B, n = h->n, L = h->L;
   size_t zoff[ICNN_MAX_LAYERS], doff[2];
-  ws_floats(h, B, zoff, doff);
+  picnn_simt_ws_floats(h, B, zoff, doff);
   float* ws = static_cast<float*>(workspace);
   float* Z[ICNN_MAX_LAYERS];
   for (int i = 0; i < L; ++i) Z[i] = ws + zoff[i];
@@ -312,14 +341,7 @@ int picnn_fg_simt(const icnn_picnn* h, const icnn_gates* gt, const float* y32, f
     cudaError_t le = launch_gemm<0>(a, st);
     if (le != cudaSuccess) { set_error("gated_gemm<0> launch: %s", cudaGetErrorString(le)); return ICNN_E_CUDA; }
   }
-  {
-    OutArgs o{};
-    o.M = B; o.S = h->hidden[L - 1]; o.n = n; o.Z = Z[L - 1]; o.Cz = gt->cz[L]; o.y = y32; o.Cy = gt->cy[L];
-    o.D = gt->d[L]; o.w = h->Wcat[L]; o.in_scale = gt->in_scale; o.in_shift = gt->in_shift;
-    o.g_scale = gt->g_scale; o.alpha = h->alpha; o.f = f; o.delta = dl[0];
-    o.g = g; o.g_row_stride = g_row_stride; o.perm = perm; o.count = count; o.KS = KS; o.skip_if_zero = skip;
-    out_layer_kernel<<<cdiv(B * 32, 256), 256, 0, st>>>(o);
-  }
+  out_layer_launch(h, gt, Z[L - 1], y32, f, dl[0], nullptr, nullptr, g, g_row_stride, perm, count, KS, skip, st);
   int cur = 0;
   for (int i = L - 1; i >= 0; --i) {  // backward hidden layers
     GemmArgs a{};
@@ -338,6 +360,16 @@ int picnn_fg_simt(const icnn_picnn* h, const icnn_gates* gt, const float* y32, f
   return ICNN_OK;
 }
 
+// K1 dispatch: tcgen05 path for TMA-compatible shapes (every width % 4 == 0) with enough rows to
+// fill a 128-row tile, FP32 FFMA path otherwise.  ICNN_K1=simt|tc forces one.
+int picnn_fg_dispatch(const icnn_picnn* h, const icnn_gates* gt, const float* y32, float* f, float* g,
+                      long long g_row_stride, const int* perm, const int* count, int KS, void* workspace,
+                      const int* skip, cudaStream_t st) {
+  if (h->use_tc && gt->B >= 64)
+    return picnn_fg_tc(h, gt, y32, f, g, g_row_stride, perm, count, KS, workspace, skip, st);
+  return picnn_fg_simt(h, gt, y32, f, g, g_row_stride, perm, count, KS, workspace, skip, st);
+}
+
 }  // namespace icnn
 
 using namespace icnn;
@@ -354,6 +386,8 @@ extern "C" int icnn_picnn_create(const icnn_picnn_desc* d, icnn_picnn_t** out, v
     h->hidden[i] = d->hidden[i];
   }
   for (int i = 0; i <= d->L; ++i) h->Wcat[i] = nullptr;
+  for (int i = 0; i < ICNN_MAX_LAYERS; ++i) h->Wb_hi[i] = h->Wb_lo[i] = h->Wf_hi[i] = h->Wf_lo[i] = nullptr;
+  h->use_tc = false;
   for (int i = 0; i <= d->L; ++i) {
     const long long si = h->width(i), sp = h->prev(i);
     const long long ntop = sp * si, nbot = (long long)h->n * si;
@@ -362,6 +396,17 @@ extern "C" int icnn_picnn_create(const icnn_picnn_desc* d, icnn_picnn_t** out, v
     if (e != cudaSuccess) { icnn_picnn_destroy(h); set_error("cudaMalloc weights: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
     const long long tot = ntop + nbot;
     concat_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->Wcat[i], d->Wz[i], ntop, d->Wy[i], nbot);
+  }
+  {
+    const char* k1 = getenv("ICNN_K1");
+    const bool want = !(k1 && k1[0] == 's');
+    if (want && picnn_tc_supported(h)) {
+      int rc = picnn_tc_prepare_weights(h, st);
+      if (rc) { icnn_picnn_destroy(h); return rc; }
+      h->use_tc = true;
+    } else if (k1 && k1[0] == 't') {
+      icnn_picnn_destroy(h); set_error("ICNN_K1=tc but the shape is not TMA-compatible (widths %% 4)"); return ICNN_E_UNSUPPORTED;
+    }
   }
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) { icnn_picnn_destroy(h); set_error("picnn_create: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
@@ -373,13 +418,15 @@ extern "C" int icnn_picnn_destroy(icnn_picnn_t* h) {
   if (!h) return ICNN_OK;
   for (int i = 0; i <= h->L && i <= ICNN_MAX_LAYERS; ++i)
     if (h->Wcat[i]) cudaFree(h->Wcat[i]);
+  picnn_tc_free_weights(h);
   delete h;
   return ICNN_OK;
 }
 
 extern "C" size_t icnn_picnn_workspace_bytes(const icnn_picnn_t* h, int32_t B) {
   if (!h || B <= 0) return 0;
-  return sizeof(float) * ws_floats(h, B, nullptr, nullptr);
+  return sizeof(float) * (picnn_simt_ws_floats(h, B, nullptr, nullptr) +
+                          (h->use_tc ? picnn_tc_ws_floats(h, B, nullptr, nullptr) : 0));
 }
 
 extern "C" int icnn_picnn_fg(const icnn_picnn_t* h, const icnn_gates* gates, const float* y32, float* f,
@@ -388,8 +435,8 @@ extern "C" int icnn_picnn_fg(const icnn_picnn_t* h, const icnn_gates* gates, con
   ICNN_REQUIRE(h && gates && y32 && f && g && workspace, "null pointer");
   ICNN_REQUIRE(gates->B > 0, "empty batch");
   ICNN_REQUIRE((perm == nullptr) == (count == nullptr), "perm and count go together");
-  return picnn_fg_simt(h, gates, y32, f, g, g_row_stride, perm, count, KS, workspace, skip_if_zero,
-                       static_cast<cudaStream_t>(stream));
+  return picnn_fg_dispatch(h, gates, y32, f, g, g_row_stride, perm, count, KS, workspace, skip_if_zero,
+                           static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int icnn_gd_solve(const icnn_picnn_t* h, const icnn_gates* gates, float* y32, float* v, float* g,
@@ -401,11 +448,11 @@ extern "C" int icnn_gd_solve(const icnn_picnn_t* h, const icnn_gates* gates, flo
   const long long N = (long long)gates->B * h->n;
   ICNN_CUDA_CHECK(cudaMemsetAsync(v, 0, sizeof(float) * N, st));
   for (int it = 0; it < nIter; ++it) {
-    int rc = picnn_fg_simt(h, gates, y32, f_out, g, h->n, nullptr, nullptr, 0, workspace, nullptr, st);
+    int rc = picnn_fg_dispatch(h, gates, y32, f_out, g, h->n, nullptr, nullptr, 0, workspace, nullptr, st);
     if (rc) return rc;
     gd_update_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(y32, v, g, N, lr, momentum);
   }
-  int rc = picnn_fg_simt(h, gates, y32, f_out, g, h->n, nullptr, nullptr, 0, workspace, nullptr, st);
+  int rc = picnn_fg_dispatch(h, gates, y32, f_out, g, h->n, nullptr, nullptr, 0, workspace, nullptr, st);
   if (rc) return rc;
   ICNN_CUDA_CHECK(cudaGetLastError());
   return ICNN_OK;

@@ -1,0 +1,496 @@
+// K1 (tensor-core path): PICNN f and df/dy with tcgen05.mma (kind::tf32, 3xTF32 split for
+// FP32-level accuracy), operands staged by TMA into 128B-swizzled shared memory, accumulators in
+// TMEM, fused epilogues read back with tcgen05.ld.
+//
+// Same math as picnn_simt.cu (multi-label-cls/icnn_ebundle.py:349-387,146; RL/src/icnn.py:356-404):
+//   forward  layer i : Z_i   = act( A'_i  Wcat_i + d_i ),   A'_i = [Z_{i-1} o cz_i | (s y + t) o cy_i]
+//   backward layer i : [delta_{i-1} | g +=] = delta_i Wcat_i^T  with the gate / act' epilogues
+// Every GEMM is  C[M,N] = A[M,K] * B[N,K]^T  with BOTH operands K-major (the library keeps the
+// weights in both orientations), each operand pre-split into hi = tf32(x) and lo = x - hi:
+//   C = A_hi B_hi + A_hi B_lo + A_lo B_hi     (three tcgen05.mma per k-step, one FP32 TMEM accumulator)
+// Plain TF32 (10-bit mantissa) moves y* by 1e-3..1e-2 (hard part 2); the split
+// restores ~2^-21 relative error.
+//
+// Kernel anatomy (192 threads, one 128 x BN output tile per CTA):
+//   warp 0      TMA producer   : cp.async.bulk.tensor.2d of A_hi/A_lo/B_hi/B_lo boxes (32 fp32 = 128 B
+//                                wide) into a NST-stage ring, mbarrier expect_tx
+//   warp 1      MMA issuer     : one elected lane issues 12 tcgen05.mma per stage, tcgen05.commit
+//                                releases the stage / signals the epilogue; also owns TMEM alloc
+//   warps 2..5  epilogue       : tcgen05.ld (32 lanes x 16 columns), fused bias/activation/gates,
+//                                global stores (each warp owns TMEM lanes 32*(warp%4)..+31)
+#include "common.cuh"
+
+#include <cuda.h>
+
+namespace icnn {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  uint32_t spins = 0;
+  do {
+    if (++spins > (1u << 28)) __trap();   // a lost transaction would otherwise hang the GPU
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of 128 B, 8-row atoms
+// of 1024 B (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64)).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)0 << 16;                       // LBO: unused for a single 128B swizzle atom along K
+  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;  // SBO: 8 rows x 128 B between row atoms
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor, kind::tf32: C=F32 (bit 4), A=B=TF32 (2 at bits 7, 10), K-major both,
+// N>>3 at [17,23), M>>4 at [24,29)  (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// ---------------------------------------------------------------------------------------------
+// the GEMM kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;  // fp32 elements per stage row = one 128-byte swizzle span
+
+struct TcArgs {
+  int M, N, K;
+  int mode;  // 0 forward, 1 backward, 2 plain store (self test)
+  // forward epilogue: Z = act(acc + D); optional next-layer operand A'_{next}[:, 0:N] = Z o Cz_next (hi/lo)
+  const float* D; float* Z; float alpha;
+  const float* Cz_next; float* nxt_hi; float* nxt_lo; int nxt_ld;
+  // backward epilogue: columns < N0 -> delta_prev = act'(Zprev) o Cz o acc (hi/lo, ld N0); else g += ...
+  int N0; const float* Zprev; const float* Cz; float* dprev_hi; float* dprev_lo;
+  const float* Cy; float* g; long long g_row_stride; const int* perm; const int* count; int KS; int n;
+  float g_scale;
+  float* C;  // mode 2
+  const int* skip_if_zero;
+};
+
+template <int BN>
+struct TcSmem {
+  static constexpr int NST = (BN == 128) ? 3 : 4;
+  static constexpr int A_BYTES = TC_BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int BAR_OFF = NST * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // + alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, TcArgs a) {
+  if (a.skip_if_zero != nullptr && *a.skip_if_zero == 0) return;
+  using S = TcSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* empty = full + S::NST;
+  uint64_t* tmem_full = empty + S::NST;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int nkb = (a.K + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
+    for (int s = 0; s < S::NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);  // BN fp32 accumulator columns (power of two >= 32)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S::NST;
+        const uint32_t ph = (kb / S::NST) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], S::STAGE_BYTES);
+        uint8_t* st = smem + s * S::STAGE_BYTES;
+        tma_load_2d(st, &tmAh, &full[s], kb * TC_BK, m0);
+        tma_load_2d(st + S::A_BYTES, &tmAl, &full[s], kb * TC_BK, m0);
+        tma_load_2d(st + 2 * S::A_BYTES, &tmBh, &full[s], kb * TC_BK, n0);
+        tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, &full[s], kb * TC_BK, n0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S::NST;
+        const uint32_t ph = (kb / S::NST) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint64_t dAh = make_kmajor_sw128_desc(st);
+        const uint64_t dAl = make_kmajor_sw128_desc(st + S::A_BYTES);
+        const uint64_t dBh = make_kmajor_sw128_desc(st + 2 * S::A_BYTES);
+        const uint64_t dBl = make_kmajor_sw128_desc(st + 2 * S::A_BYTES + S::B_BYTES);
+#pragma unroll
+        for (int k4 = 0; k4 < TC_BK / 8; ++k4) {
+          const uint64_t adv = (uint64_t)((k4 * 8 * 4) >> 4);  // +32 B per k-step inside the swizzle span
+          umma_tf32(tmem_base, dAh + adv, dBh + adv, idesc, (kb | k4) ? 1u : 0u);
+          umma_tf32(tmem_base, dAh + adv, dBl + adv, idesc, 1u);
+          umma_tf32(tmem_base, dAl + adv, dBh + adv, idesc, 1u);
+        }
+        umma_commit(&empty[s]);  // stage free once these MMAs have read it
+      }
+      umma_commit(tmem_full);    // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue: TMEM -> registers -> fused epilogue -> global ----
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int m = m0 + q * 32 + lane;     // output row owned by this thread
+    const bool mv = m < a.M;
+    float* grow = nullptr;
+    if (a.mode == 1 && mv) {
+      if (a.perm == nullptr) grow = a.g + (long long)m * a.g_row_stride;
+      else grow = a.g + ((long long)m * a.KS + a.perm[(long long)m * a.KS + a.count[m]]) * a.n;
+    }
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (!mv) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int nn = n0 + c0 + j;
+        if (nn >= a.N) break;
+        const float acc = __uint_as_float(v[j]);
+        if (a.mode == 0) {
+          const float x = acc + a.D[(long long)m * a.N + nn];
+          const float z = x > 0.f ? x : a.alpha * x;
+          a.Z[(long long)m * a.N + nn] = z;
+          if (a.nxt_hi) {
+            const float p = z * a.Cz_next[(long long)m * a.N + nn];
+            const float h = tf32_hi(p);
+            a.nxt_hi[(long long)m * a.nxt_ld + nn] = h;
+            a.nxt_lo[(long long)m * a.nxt_ld + nn] = p - h;
+          }
+        } else if (a.mode == 1) {
+          if (nn < a.N0) {
+            const long long idx = (long long)m * a.N0 + nn;
+            const float da = a.Zprev[idx] > 0.f ? 1.f : a.alpha;
+            const float p = da * a.Cz[idx] * acc;
+            const float h = tf32_hi(p);
+            a.dprev_hi[idx] = h;
+            a.dprev_lo[idx] = p - h;
+          } else {
+            const int e = nn - a.N0;
+            grow[e] = fmaf(a.g_scale * a.Cy[(long long)m * a.n + e], acc, grow[e]);
+          }
+        } else {
+          a.C[(long long)m * a.N + nn] = acc;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise helpers
+// ---------------------------------------------------------------------------------------------
+// A'_i[:, off + e] = ((s*y + t) o cy_i)[e] split into hi/lo, for all layers in one launch
+struct GateYArgs {
+  int B, n, L;
+  const float* y; float sc, sh;
+  const float* cy[ICNN_MAX_LAYERS]; float* hi[ICNN_MAX_LAYERS]; float* lo[ICNN_MAX_LAYERS];
+  int ld[ICNN_MAX_LAYERS]; int off[ICNN_MAX_LAYERS];
+  const int* skip_if_zero;
+};
+__global__ void gate_y_kernel(GateYArgs a) {
+  if (a.skip_if_zero != nullptr && *a.skip_if_zero == 0) return;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)a.B * a.n) return;
+  const int m = (int)(i / a.n), e = (int)(i % a.n);
+  const float yy = fmaf(a.sc, a.y[i], a.sh);
+  for (int l = 0; l < a.L; ++l) {
+    const float p = yy * a.cy[l][i];
+    const float h = tf32_hi(p);
+    a.hi[l][(long long)m * a.ld[l] + a.off[l] + e] = h;
+    a.lo[l][(long long)m * a.ld[l] + a.off[l] + e] = p - h;
+  }
+}
+
+__global__ void split_tf32_kernel(const float* src, float* hi, float* lo, long long N) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float x = src[i], h = tf32_hi(x);
+  hi[i] = h;
+  lo[i] = x - h;
+}
+// dst[c, r] = src[r, c] split hi/lo   (src [R, C] row-major -> dst [C, R])
+__global__ void transpose_split_kernel(const float* src, float* hi, float* lo, int R, int C) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? src[(long long)r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < R) {
+      const float x = tile[threadIdx.x][i], h = tf32_hi(x);
+      hi[(long long)c * R + r] = h;
+      lo[(long long)c * R + r] = x - h;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] (cols contiguous, row pitch ld floats), box = [box_rows, 32 cols], 128B swizzle
+static int make_tmap(CUtensorMap* tm, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ICNN_E_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld); return ICNN_E_CUDA; }
+  return ICNN_OK;
+}
+
+static int launch_tc_gemm(const float* Ah, const float* Al, long long lda, const float* Bh, const float* Bl, long long ldb,
+                          TcArgs a, cudaStream_t st) {
+  const int gy = cdiv(a.M, TC_BM);
+  const bool wide = (cdiv(a.N, 128) * gy >= 148) && (a.N >= 128);
+  const int BN = wide ? 128 : 64;
+  CUtensorMap tAh, tAl, tBh, tBl;
+  int rc;
+  if ((rc = make_tmap(&tAh, Ah, a.M, a.K, lda, TC_BM))) return rc;
+  if ((rc = make_tmap(&tAl, Al, a.M, a.K, lda, TC_BM))) return rc;
+  if ((rc = make_tmap(&tBh, Bh, a.N, a.K, ldb, BN))) return rc;
+  if ((rc = make_tmap(&tBl, Bl, a.N, a.K, ldb, BN))) return rc;
+  dim3 grid(cdiv(a.N, BN), gy);
+  cudaError_t e;
+  if (BN == 128) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128>::TOTAL); attr = true; }
+    tc_gemm_kernel<128><<<grid, 192, TcSmem<128>::TOTAL, st>>>(tAh, tAl, tBh, tBl, a);
+  } else {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(tc_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64>::TOTAL); attr = true; }
+    tc_gemm_kernel<64><<<grid, 192, TcSmem<64>::TOTAL, st>>>(tAh, tAl, tBh, tBl, a);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("tc_gemm launch: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
+  return ICNN_OK;
+}
+
+// shapes the tensor-core path accepts: every contraction / leading dimension a multiple of 4
+// floats (16-byte TMA strides)
+bool picnn_tc_supported(const icnn_picnn* h) {
+  if (h->n % 4) return false;
+  for (int i = 0; i < h->L; ++i) if (h->hidden[i] % 4) return false;
+  return get_encode() != nullptr;
+}
+
+int picnn_tc_prepare_weights(icnn_picnn* h, cudaStream_t st) {
+  for (int i = 0; i < h->L; ++i) {  // hidden layers only; the width-1 output layer stays on the SIMT kernel
+    const int si = h->hidden[i], kf = h->prev(i) + h->n;
+    const size_t bytes = sizeof(float) * (size_t)kf * si;
+    for (float** p : {&h->Wb_hi[i], &h->Wb_lo[i], &h->Wf_hi[i], &h->Wf_lo[i]}) {
+      cudaError_t e = cudaMalloc(p, bytes);
+      if (e != cudaSuccess) { set_error("cudaMalloc tc weights: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
+    }
+    const long long N = (long long)kf * si;
+    split_tf32_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(h->Wcat[i], h->Wb_hi[i], h->Wb_lo[i], N);
+    dim3 tb(32, 8), tg(cdiv(si, 32), cdiv(kf, 32));
+    transpose_split_kernel<<<tg, tb, 0, st>>>(h->Wcat[i], h->Wf_hi[i], h->Wf_lo[i], kf, si);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("tc weight prep: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
+  return ICNN_OK;
+}
+
+void picnn_tc_free_weights(icnn_picnn* h) {
+  for (int i = 0; i < ICNN_MAX_LAYERS; ++i)
+    for (float** p : {&h->Wb_hi[i], &h->Wb_lo[i], &h->Wf_hi[i], &h->Wf_lo[i]})
+      if (*p) { cudaFree(*p); *p = nullptr; }
+}
+
+// extra workspace (floats) after the SIMT part: per hidden layer A'_i hi/lo [B, s_{i-1}+n]; delta hi/lo x2
+size_t picnn_tc_ws_floats(const icnn_picnn* h, int B, size_t* aoff, size_t* doff) {
+  size_t off = 0;
+  int smax = 0;
+  auto al = [](size_t v) { return (v + 63) & ~(size_t)63; };
+  for (int i = 0; i < h->L; ++i) {
+    const size_t sz = al((size_t)B * (h->prev(i) + h->n));
+    if (aoff) { aoff[2 * i] = off; aoff[2 * i + 1] = off + sz; }
+    off += 2 * sz;
+    smax = h->hidden[i] > smax ? h->hidden[i] : smax;
+  }
+  const size_t dsz = al((size_t)B * smax);
+  if (doff) for (int j = 0; j < 4; ++j) doff[j] = off + j * dsz;
+  off += 4 * dsz;
+  return off;
+}
+
+void out_layer_launch(const icnn_picnn* h, const icnn_gates* gt, const float* Zlast, const float* y32, float* f,
+                      float* delta, float* delta_hi, float* delta_lo, float* g, long long g_row_stride,
+                      const int* perm, const int* count, int KS, const int* skip, cudaStream_t st);
+size_t picnn_simt_ws_floats(const icnn_picnn* h, int B, size_t* zoff, size_t* doff);
+
+int picnn_fg_tc(const icnn_picnn* h, const icnn_gates* gt, const float* y32, float* f, float* g,
+                long long g_row_stride, const int* perm, const int* count, int KS, void* workspace,
+                const int* skip, cudaStream_t st) {
+  const int B = gt->B, n = h->n, L = h->L;
+  size_t zoff[ICNN_MAX_LAYERS], sdoff[2], aoff[2 * ICNN_MAX_LAYERS], doff[4];
+  const size_t simt = picnn_simt_ws_floats(h, B, zoff, sdoff);
+  picnn_tc_ws_floats(h, B, aoff, doff);
+  float* ws = static_cast<float*>(workspace);
+  float* tcw = ws + simt;
+  float* Z[ICNN_MAX_LAYERS];
+  float *Ah[ICNN_MAX_LAYERS], *Al[ICNN_MAX_LAYERS];
+  for (int i = 0; i < L; ++i) { Z[i] = ws + zoff[i]; Ah[i] = tcw + aoff[2 * i]; Al[i] = tcw + aoff[2 * i + 1]; }
+  float* dh[2] = {tcw + doff[0], tcw + doff[2]};
+  float* dl[2] = {tcw + doff[1], tcw + doff[3]};
+
+  {  // (s y + t) o cy_i for every hidden layer, straight into the K-concatenated operands
+    GateYArgs ga{};
+    ga.B = B; ga.n = n; ga.L = L; ga.y = y32; ga.sc = gt->in_scale; ga.sh = gt->in_shift; ga.skip_if_zero = skip;
+    for (int i = 0; i < L; ++i) { ga.cy[i] = gt->cy[i]; ga.hi[i] = Ah[i]; ga.lo[i] = Al[i]; ga.ld[i] = h->prev(i) + n; ga.off[i] = h->prev(i); }
+    const long long N = (long long)B * n;
+    gate_y_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ga);
+  }
+  for (int i = 0; i < L; ++i) {
+    TcArgs a{};
+    a.M = B; a.N = h->hidden[i]; a.K = h->prev(i) + n; a.mode = 0;
+    a.D = gt->d[i]; a.Z = Z[i]; a.alpha = h->alpha; a.skip_if_zero = skip;
+    if (i + 1 < L) { a.Cz_next = gt->cz[i + 1]; a.nxt_hi = Ah[i + 1]; a.nxt_lo = Al[i + 1]; a.nxt_ld = h->hidden[i] + n; }
+    int rc = launch_tc_gemm(Ah[i], Al[i], a.K, h->Wf_hi[i], h->Wf_lo[i], a.K, a, st);
+    if (rc) return rc;
+  }
+  out_layer_launch(h, gt, Z[L - 1], y32, f, nullptr, dh[0], dl[0], g, g_row_stride, perm, count, KS, skip, st);
+  int cur = 0;
+  for (int i = L - 1; i >= 0; --i) {
+    TcArgs a{};
+    a.M = B; a.N0 = h->prev(i); a.N = a.N0 + n; a.K = h->hidden[i]; a.mode = 1; a.alpha = h->alpha;
+    a.Zprev = i ? Z[i - 1] : nullptr; a.Cz = i ? gt->cz[i] : nullptr; a.dprev_hi = dh[cur ^ 1]; a.dprev_lo = dl[cur ^ 1];
+    a.Cy = gt->cy[i]; a.g = g; a.g_row_stride = g_row_stride; a.perm = perm; a.count = count; a.KS = KS; a.n = n;
+    a.g_scale = gt->g_scale; a.skip_if_zero = skip;
+    int rc = launch_tc_gemm(dh[cur], dl[cur], a.K, h->Wb_hi[i], h->Wb_lo[i], a.K, a, st);
+    if (rc) return rc;
+    cur ^= 1;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("picnn_fg_tc launch: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
+  return ICNN_OK;
+}
+
+}  // namespace icnn
+
+using namespace icnn;
+
+// Self test of the tensor-core GEMM: C[M,N] = A[M,K] * B[N,K]^T (3xTF32), all device, row-major.
+// scratch: 2*M*K + 2*N*K floats.
+extern "C" int icnn_tc_gemm_selftest(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
+                                     float* scratch, void* stream) {
+  ICNN_REQUIRE(A && B && C && scratch, "null pointer");
+  ICNN_REQUIRE(M > 0 && N > 0 && K > 0 && K % 4 == 0, "need K % 4 == 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* Ah = scratch; float* Al = Ah + (size_t)M * K; float* Bh = Al + (size_t)M * K; float* Bl = Bh + (size_t)N * K;
+  split_tf32_kernel<<<(unsigned)(((long long)M * K + 255) / 256), 256, 0, st>>>(A, Ah, Al, (long long)M * K);
+  split_tf32_kernel<<<(unsigned)(((long long)N * K + 255) / 256), 256, 0, st>>>(B, Bh, Bl, (long long)N * K);
+  TcArgs a{};
+  a.M = M; a.N = N; a.K = K; a.mode = 2; a.C = C;
+  return launch_tc_gemm(Ah, Al, K, Bh, Bl, K, a, st);
+}

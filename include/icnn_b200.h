@@ -153,6 +153,13 @@ int icnn_gd_solve(const icnn_picnn_t* h, const icnn_gates* gates, float* y32, fl
                   float* f_out, int32_t nIter, float lr, float momentum, void* workspace,
                   void* stream);
 
+/* ---- diagnostics ------------------------------------------------------------------------------ */
+/* Self test of the tcgen05 / TMA GEMM the tensor-core K1 path is built from:
+ * C[M,N] = A[M,K] * B[N,K]^T with the 3xTF32 split (all row-major device buffers, K % 4 == 0;
+ * scratch holds 2*M*K + 2*N*K floats). */
+int icnn_tc_gemm_selftest(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
+                          float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
