@@ -158,7 +158,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);  // BN fp32 accumulator columns (power of two >= 32)
+  // Four FP32 accumulators of BN columns each: the tensor core rounds its accumulator toward zero
+  // on every MMA, so one accumulator over K=2048 (768 sequential adds with the 3xTF32 split) drifts
+  // to ~2e-5 relative (measured).  The hi*hi products rotate over accumulators 0..2, the 2^-11
+  // smaller cross terms go to accumulator 3, and the epilogue adds the four in FP32 (RN).
+  if (warp == 1) tmem_alloc(tmem_slot, 4 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -195,9 +199,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
         for (int k4 = 0; k4 < TC_BK / 8; ++k4) {
           const uint64_t adv = (uint64_t)((k4 * 8 * 4) >> 4);  // +32 B per k-step inside the swizzle span
-          umma_tf32(tmem_base, dAh + adv, dBh + adv, idesc, (kb | k4) ? 1u : 0u);
-          umma_tf32(tmem_base, dAh + adv, dBl + adv, idesc, 1u);
-          umma_tf32(tmem_base, dAl + adv, dBh + adv, idesc, 1u);
+          const int step = kb * (TC_BK / 8) + k4;
+          const uint32_t hh = tmem_base + (uint32_t)((step % 3) * BN);
+          const uint32_t xx = tmem_base + (uint32_t)(3 * BN);
+          umma_tf32(hh, dAh + adv, dBh + adv, idesc, step >= 3 ? 1u : 0u);
+          umma_tf32(xx, dAh + adv, dBl + adv, idesc, step ? 1u : 0u);
+          umma_tf32(xx, dAl + adv, dBh + adv, idesc, 1u);
         }
         umma_commit(&empty[s]);  // stage free once these MMAs have read it
       }
@@ -216,9 +223,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       if (a.perm == nullptr) grow = a.g + (long long)m * a.g_row_stride;
       else grow = a.g + ((long long)m * a.KS + a.perm[(long long)m * a.KS + a.count[m]]) * a.n;
     }
+    const int nsteps = nkb * (TC_BK / 8);
     for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      uint32_t v[16], w[16];
+      const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      tmem_ld16(tb, v);                                  // hi*hi accumulator 0 (always written)
+      if (nsteps > 1) {
+        tmem_ld16(tb + BN, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+      }
+      if (nsteps > 2) {
+        tmem_ld16(tb + 2 * BN, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+      }
+      tmem_ld16(tb + 3 * BN, w);                         // cross terms
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
       if (!mv) continue;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -257,7 +279,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 4 * BN);
   }
 }
 
