@@ -286,35 +286,38 @@ __device__ inline void gram_pass_simt(const Grp<WPS>& g, const float* const* row
 }
 
 // gram pass on the FP64 tensor cores (n % 4 == 0): every warp sweeps its own 16-column groups
-// for ALL 8x8 tiles of the upper triangle (each row is read exactly once per pass), one
-// 128-bit load per lane per row block -- lane (r, q) = (lane/4, lane%4) gets columns 4q..4q+3
-// of row 8*rb + r, which are its A/B fragment elements for four consecutive k-steps (the four
-// columns of a k-step may be any four, as long as A, B and w agree).  Warp partials are then
-// added into M in warp order (deterministic).
-template <int WPS, int RB>
-__device__ inline void gram_sweep_dmma(const Grp<WPS>& g, const float* const* rowp, int k, int n,
-                                       const double* w, double* M, int ld) {
-  constexpr int NT = RB * (RB + 1) / 2;
+// for a rectangle of 8x8 tiles (row blocks a0..a0+NA-1 x b0..b0+NB-1; TRI: a0 == b0 and only the
+// upper triangle), so each row of the rectangle is read once per sweep with one 128-bit load
+// per lane per row block -- lane (r, q) = (lane/4, lane%4) gets columns 4q..4q+3 of row
+// 8*blk + r, which are its A/B fragment elements for four consecutive k-steps (the four columns
+// of a k-step may be any four, as long as A, B and w agree).  Warp partials are then added into
+// M in warp order (deterministic).
+template <int WPS, int NA, int NB, bool TRI>
+__device__ inline void gram_sweep(const Grp<WPS>& g, const float* const* rowp, int k, int n,
+                                  const double* w, double* M, int ld, int a0, int b0) {
+  constexpr int NT = TRI ? NA * (NA + 1) / 2 : NA * NB;
+  constexpr int NL = TRI ? NB : NA + NB;   // row blocks to load (TRI: A and B blocks coincide)
   double acc[NT][2];
 #pragma unroll
   for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
   const int r = g.lane >> 2, q = g.lane & 3;
-  const float* rp[RB];
-  bool rv_[RB];
+  const float* rp[NL];
+  bool rok[NL];
 #pragma unroll
-  for (int b = 0; b < RB; ++b) {
-    const int row = b * 8 + r;
-    rv_[b] = row < k;
-    rp[b] = rowp[rv_[b] ? row : k - 1] + 4 * q;
+  for (int b = 0; b < NL; ++b) {
+    const int blk = TRI ? (b0 + b) : (b < NA ? a0 + b : b0 + (b - NA));
+    const int row = blk * 8 + r;
+    rok[b] = row < k;
+    rp[b] = rowp[rok[b] ? row : k - 1] + 4 * q;
   }
   const int ngrp = (n + 15) >> 4;
   for (int gi = g.warp; gi < ngrp; gi += WPS) {
     const int col = gi * 16 + 4 * q;
     const bool cv = col < n;  // n % 4 == 0: the whole float4 is in or out
-    float4 v[RB];
+    float4 v[NL];
 #pragma unroll
-    for (int b = 0; b < RB; ++b)
-      v[b] = (cv && rv_[b]) ? __ldg(reinterpret_cast<const float4*>(rp[b] + gi * 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < NL; ++b)
+      v[b] = (cv && rok[b]) ? __ldg(reinterpret_cast<const float4*>(rp[b] + gi * 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
     double wv[4];
     if (cv) {
       const double2 w01 = *reinterpret_cast<const double2*>(w + col);
@@ -325,35 +328,34 @@ __device__ inline void gram_sweep_dmma(const Grp<WPS>& g, const float* const* ro
     }
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-      double bf[RB], af[RB];
+      double f[NL];
 #pragma unroll
-      for (int b = 0; b < RB; ++b) {
-        const float f = (s == 0) ? v[b].x : (s == 1) ? v[b].y : (s == 2) ? v[b].z : v[b].w;
-        bf[b] = (double)f;
-        af[b] = bf[b] * wv[s];
-      }
+      for (int b = 0; b < NL; ++b)
+        f[b] = (double)((s == 0) ? v[b].x : (s == 1) ? v[b].y : (s == 2) ? v[b].z : v[b].w);
       int t = 0;
 #pragma unroll
-      for (int bi = 0; bi < RB; ++bi)
+      for (int i = 0; i < NA; ++i) {
+        const double af = f[i] * wv[s];   // A fragment carries the weight
 #pragma unroll
-        for (int bj = bi; bj < RB; ++bj) { dmma884(acc[t][0], acc[t][1], af[bi], bf[bj]); ++t; }
+        for (int j = TRI ? i : 0; j < NB; ++j) { dmma884(acc[t][0], acc[t][1], af, f[TRI ? j : NA + j]); ++t; }
+      }
     }
   }
   // ordered accumulation of the warp partials into M (symmetric fill)
-  for (int wv_i = 0; wv_i < WPS; ++wv_i) {
-    if (g.warp == wv_i) {
+  for (int wi = 0; wi < WPS; ++wi) {
+    if (g.warp == wi) {
       int t = 0;
 #pragma unroll
-      for (int bi = 0; bi < RB; ++bi)
+      for (int i = 0; i < NA; ++i)
 #pragma unroll
-        for (int bj = bi; bj < RB; ++bj) {
+        for (int j = TRI ? i : 0; j < NB; ++j) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int i = bi * 8 + r, j = bj * 8 + 2 * q + h;
-            if (i < k && j < k && (bi != bj || j >= i)) {
-              const double val = (wv_i == 0 ? 0.0 : M[i * ld + j]) + acc[t][h];
-              M[i * ld + j] = val;
-              M[j * ld + i] = val;
+            const int ii = (a0 + i) * 8 + r, jj = (b0 + j) * 8 + 2 * q + h;
+            if (ii < k && jj < k && (!(TRI && i == j) || jj >= ii)) {
+              const double val = (wi == 0 ? 0.0 : M[ii * ld + jj]) + acc[t][h];
+              M[ii * ld + jj] = val;
+              M[jj * ld + ii] = val;
             }
           }
           ++t;
@@ -363,15 +365,31 @@ __device__ inline void gram_sweep_dmma(const Grp<WPS>& g, const float* const* ro
   }
 }
 
+template <int WPS, int NB>
+__device__ inline void gram_rect_pair(const Grp<WPS>& g, const float* const* rowp, int k, int n,
+                                      const double* w, double* M, int ld) {
+  gram_sweep<WPS, 2, NB, false>(g, rowp, k, n, w, M, ld, 0, 4);
+  gram_sweep<WPS, 2, NB, false>(g, rowp, k, n, w, M, ld, 2, 4);
+}
+
 template <int WPS>
 __device__ inline void gram_pass(const Grp<WPS>& g, const float* const* rowp, int k, int n,
                                  const double* w, double* M, int ld) {
-  if ((n & 3) != 0 || k > 32) { gram_pass_simt<WPS>(g, rowp, k, n, w, M, ld); g.sync(); return; }
-  const int rb = (k + 7) >> 3;
-  if (rb == 1) gram_sweep_dmma<WPS, 1>(g, rowp, k, n, w, M, ld);
-  else if (rb == 2) gram_sweep_dmma<WPS, 2>(g, rowp, k, n, w, M, ld);
-  else if (rb == 3) gram_sweep_dmma<WPS, 3>(g, rowp, k, n, w, M, ld);
-  else gram_sweep_dmma<WPS, 4>(g, rowp, k, n, w, M, ld);
+  if ((n & 3) != 0) { gram_pass_simt<WPS>(g, rowp, k, n, w, M, ld); g.sync(); return; }
+  const int rb = (k + 7) >> 3;   // <= 8 (KS <= 64)
+  if (rb == 1) gram_sweep<WPS, 1, 1, true>(g, rowp, k, n, w, M, ld, 0, 0);
+  else if (rb == 2) gram_sweep<WPS, 2, 2, true>(g, rowp, k, n, w, M, ld, 0, 0);
+  else if (rb == 3) gram_sweep<WPS, 3, 3, true>(g, rowp, k, n, w, M, ld, 0, 0);
+  else {
+    gram_sweep<WPS, 4, 4, true>(g, rowp, k, n, w, M, ld, 0, 0);
+    if (rb > 4) {   // rows 32..k-1: second triangle + the 4 x (rb-4) rectangle in two halves
+      const int r2 = rb - 4;
+      if (r2 == 1) { gram_sweep<WPS, 1, 1, true>(g, rowp, k, n, w, M, ld, 4, 4); gram_rect_pair<WPS, 1>(g, rowp, k, n, w, M, ld); }
+      else if (r2 == 2) { gram_sweep<WPS, 2, 2, true>(g, rowp, k, n, w, M, ld, 4, 4); gram_rect_pair<WPS, 2>(g, rowp, k, n, w, M, ld); }
+      else if (r2 == 3) { gram_sweep<WPS, 3, 3, true>(g, rowp, k, n, w, M, ld, 4, 4); gram_rect_pair<WPS, 3>(g, rowp, k, n, w, M, ld); }
+      else { gram_sweep<WPS, 4, 4, true>(g, rowp, k, n, w, M, ld, 4, 4); gram_rect_pair<WPS, 4>(g, rowp, k, n, w, M, ld); }
+    }
+  }
 }
 
 // ---- the step kernel ----------------------------------------------------------------------

@@ -85,6 +85,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of 128 B, 8-row atoms
 // of 1024 B (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64)).
@@ -212,47 +225,59 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
     __syncwarp();
   } else {
-    // ---- epilogue: TMEM -> registers -> fused epilogue -> global ----
+    // ---- epilogue: TMEM -> registers -> shared-memory transpose -> fused epilogue -> global ----
+    // tcgen05.ld gives every thread one ROW of the tile; global traffic wants one row per WARP
+    // instruction (lanes = consecutive columns).  Each epilogue warp transposes 32x32 chunks through
+    // a padded tile carved out of the (now idle) stage-0 operand buffer.
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const int q = warp & 3;               // TMEM lane quarter this warp may access
-    const int m = m0 + q * 32 + lane;     // output row owned by this thread
-    const bool mv = m < a.M;
-    float* grow = nullptr;
-    if (a.mode == 1 && mv) {
-      if (a.perm == nullptr) grow = a.g + (long long)m * a.g_row_stride;
-      else grow = a.g + ((long long)m * a.KS + a.perm[(long long)m * a.KS + a.count[m]]) * a.n;
-    }
+    float* tile = reinterpret_cast<float*>(smem) + q * (32 * 33);
     const int nsteps = nkb * (TC_BK / 8);
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t v[16], w[16];
+    // bundle-slot row pointer of the row this lane would own (backward mode), broadcast by shuffle
+    unsigned long long growp = 0;
+    if (a.mode == 1) {
+      const int mr = m0 + q * 32 + lane;
+      if (mr < a.M) {
+        float* gp = (a.perm == nullptr) ? a.g + (long long)mr * a.g_row_stride
+                                        : a.g + ((long long)mr * a.KS + a.perm[(long long)mr * a.KS + a.count[mr]]) * a.n;
+        growp = reinterpret_cast<unsigned long long>(gp);
+      }
+    }
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= a.N) break;          // warp-uniform: whole chunk out of range
+      uint32_t v[32], w[32];
       const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      tmem_ld16(tb, v);                                  // hi*hi accumulator 0 (always written)
+      tmem_ld32(tb, v);                                  // hi*hi accumulator 0 (always written)
       if (nsteps > 1) {
-        tmem_ld16(tb + BN, w);
+        tmem_ld32(tb + BN, w);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
       }
       if (nsteps > 2) {
-        tmem_ld16(tb + 2 * BN, w);
+        tmem_ld32(tb + 2 * BN, w);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
       }
-      tmem_ld16(tb + 3 * BN, w);                         // cross terms
+      tmem_ld32(tb + 3 * BN, w);                         // cross terms
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
-      if (!mv) continue;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int nn = n0 + c0 + j;
-        if (nn >= a.N) break;
-        const float acc = __uint_as_float(v[j]);
+      for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
+      __syncwarp();
+      const int nn = n0 + c0 + lane;                     // this lane's column for the whole chunk
+      const bool nv = nn < a.N;
+      for (int rr = 0; rr < 32; ++rr) {
+        const int m = m0 + q * 32 + rr;
+        if (m >= a.M) break;                             // warp-uniform
+        const float acc = tile[rr * 33 + lane];
+        const unsigned long long gp = __shfl_sync(0xffffffffu, growp, rr);
+        if (!nv) continue;
         if (a.mode == 0) {
-          const float x = acc + a.D[(long long)m * a.N + nn];
+          const long long idx = (long long)m * a.N + nn;
+          const float x = acc + a.D[idx];
           const float z = x > 0.f ? x : a.alpha * x;
-          a.Z[(long long)m * a.N + nn] = z;
+          a.Z[idx] = z;
           if (a.nxt_hi) {
-            const float p = z * a.Cz_next[(long long)m * a.N + nn];
+            const float p = z * a.Cz_next[idx];
             const float h = tf32_hi(p);
             a.nxt_hi[(long long)m * a.nxt_ld + nn] = h;
             a.nxt_lo[(long long)m * a.nxt_ld + nn] = p - h;
@@ -267,12 +292,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             a.dprev_lo[idx] = p - h;
           } else {
             const int e = nn - a.N0;
+            float* grow = reinterpret_cast<float*>(gp);
             grow[e] = fmaf(a.g_scale * a.Cy[(long long)m * a.n + e], acc, grow[e]);
           }
         } else {
           a.C[(long long)m * a.N + nn] = acc;
         }
       }
+      __syncwarp();
     }
     tc_fence_before();
   }
