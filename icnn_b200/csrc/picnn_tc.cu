@@ -265,38 +265,67 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       __syncwarp();
       const int nn = n0 + c0 + lane;                     // this lane's column for the whole chunk
       const bool nv = nn < a.N;
-      for (int rr = 0; rr < 32; ++rr) {
-        const int m = m0 + q * 32 + rr;
-        if (m >= a.M) break;                             // warp-uniform
-        const float acc = tile[rr * 33 + lane];
-        const unsigned long long gp = __shfl_sync(0xffffffffu, growp, rr);
-        if (!nv) continue;
-        if (a.mode == 0) {
-          const long long idx = (long long)m * a.N + nn;
-          const float x = acc + a.D[idx];
-          const float z = x > 0.f ? x : a.alpha * x;
-          a.Z[idx] = z;
-          if (a.nxt_hi) {
-            const float p = z * a.Cz_next[idx];
-            const float h = tf32_hi(p);
-            a.nxt_hi[(long long)m * a.nxt_ld + nn] = h;
-            a.nxt_lo[(long long)m * a.nxt_ld + nn] = p - h;
+      // rows in groups of RG: issue every global load of the group first (they are independent
+      // and L2-latency bound with only four epilogue warps per SM), then compute and store
+      constexpr int RG = 8;
+      for (int r0 = 0; r0 < 32; r0 += RG) {
+        if (m0 + q * 32 + r0 >= a.M) break;              // warp-uniform
+        float acc[RG], in0[RG], in1[RG];
+        unsigned long long gp[RG];
+#pragma unroll
+        for (int i = 0; i < RG; ++i) {
+          const int m = m0 + q * 32 + r0 + i;
+          acc[i] = tile[(r0 + i) * 33 + lane];
+          gp[i] = __shfl_sync(0xffffffffu, growp, r0 + i);
+          in0[i] = 0.f; in1[i] = 0.f;
+          if (nv && m < a.M) {
+            if (a.mode == 0) {
+              const long long idx = (long long)m * a.N + nn;
+              in0[i] = __ldg(a.D + idx);
+              if (a.nxt_hi) in1[i] = __ldg(a.Cz_next + idx);
+            } else if (a.mode == 1) {
+              if (nn < a.N0) {
+                const long long idx = (long long)m * a.N0 + nn;
+                in0[i] = __ldg(a.Zprev + idx);
+                in1[i] = __ldg(a.Cz + idx);
+              } else {
+                const int e = nn - a.N0;
+                in0[i] = __ldg(a.Cy + (long long)m * a.n + e);
+                in1[i] = reinterpret_cast<const float*>(gp[i])[e];
+              }
+            }
           }
-        } else if (a.mode == 1) {
-          if (nn < a.N0) {
-            const long long idx = (long long)m * a.N0 + nn;
-            const float da = a.Zprev[idx] > 0.f ? 1.f : a.alpha;
-            const float p = da * a.Cz[idx] * acc;
-            const float h = tf32_hi(p);
-            a.dprev_hi[idx] = h;
-            a.dprev_lo[idx] = p - h;
+        }
+#pragma unroll
+        for (int i = 0; i < RG; ++i) {
+          const int m = m0 + q * 32 + r0 + i;
+          if (!nv || m >= a.M) continue;
+          if (a.mode == 0) {
+            const long long idx = (long long)m * a.N + nn;
+            const float x = acc[i] + in0[i];
+            const float z = x > 0.f ? x : a.alpha * x;
+            a.Z[idx] = z;
+            if (a.nxt_hi) {
+              const float p = z * in1[i];
+              const float h = tf32_hi(p);
+              a.nxt_hi[(long long)m * a.nxt_ld + nn] = h;
+              a.nxt_lo[(long long)m * a.nxt_ld + nn] = p - h;
+            }
+          } else if (a.mode == 1) {
+            if (nn < a.N0) {
+              const long long idx = (long long)m * a.N0 + nn;
+              const float da = in0[i] > 0.f ? 1.f : a.alpha;
+              const float p = da * in1[i] * acc[i];
+              const float h = tf32_hi(p);
+              a.dprev_hi[idx] = h;
+              a.dprev_lo[idx] = p - h;
+            } else {
+              const int e = nn - a.N0;
+              reinterpret_cast<float*>(gp[i])[e] = fmaf(a.g_scale * in0[i], acc[i], in1[i]);
+            }
           } else {
-            const int e = nn - a.N0;
-            float* grow = reinterpret_cast<float*>(gp);
-            grow[e] = fmaf(a.g_scale * a.Cy[(long long)m * a.n + e], acc, grow[e]);
+            a.C[(long long)m * a.N + nn] = acc[i];
           }
-        } else {
-          a.C[(long long)m * a.N + nn] = acc;
         }
       }
       __syncwarp();
