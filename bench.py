@@ -341,15 +341,47 @@ def run_gpu(args):
                    peak=peaks["hbm_gbs"], unit="GB/s", traffic=None, launches=its,
                    ms_per_launch=k2_ms / max(its, 1), share_of_step=k2_ms / (k1_ms + k2_ms))
     roof_k2["frac"] = roof_k2["achieved"] / roof_k2["peak"]
-    roof_k1 = dict(kernel="gated_gemm_kernel+out_layer_kernel (PICNN f/grad, FP32 FFMA)", bound="tensor",
+    k1_name = ("tc_gemm_kernel (tcgen05 3xTF32 + TMA) + gate_y + out_layer" if int(os.environ.get("ICNN_K1", "t")[0] != "s")
+               and n % 4 == 0 and all(hh % 4 == 0 for hh in cfg["hidden"]) else "gated_gemm_kernel + out_layer (FP32 FFMA)")
+    roof_k1 = dict(kernel=k1_name, bound="tensor",
                    achieved=k1_flops / (k1_ms * 1e-3) / 1e12, peak=peaks["bf16_sustained"], unit="TFLOP/s",
-                   traffic=None, launches=its * (2 * len(cfg["hidden"]) + 1),
-                   ms_per_launch=k1_ms / max(its * (2 * len(cfg["hidden"]) + 1), 1),
+                   traffic=None, launches=its * (2 * len(cfg["hidden"]) + 2),
+                   ms_per_launch=k1_ms / max(its * (2 * len(cfg["hidden"]) + 2), 1),
                    share_of_step=k1_ms / (k1_ms + k2_ms))
     roof_k1["frac"] = roof_k1["achieved"] / roof_k1["peak"]
     dominant = roof_k2 if k2_ms >= k1_ms else roof_k1
     dominant = dict(dominant, peak_source=peaks["source"])
 
+    # ---- secondary: the north-star target shape T (batch 4096 / n_y 512), device-resident ----
+    extra_T = None
+    if args.workload != "T" and not args.no_target_shape:
+        cT = workloads.CONFIGS["T"]
+        pT, xT, y0T = workloads.make_inputs("T", seed=cT["seed"] + 7919 * rank)
+        netT = icnn_b200.PICNN.from_params(pT, device=dev)
+        fgT = netT.bind(torch.from_numpy(xT.astype(np.float32)).to(dev))
+        KST = min(cT["nIter"], cT["n"]) + 1
+        cfT = bundle_entropy._make_cfg("lib", solver, cT["nIter"], None, None, 0, cT["n"], KST)
+        stT = bundle_entropy.BundleState(cT["B"], cT["n"], KST, dev, keep_xs=True, nIter=cT["nIter"])
+        y0T_dev = torch.from_numpy(y0T).to(dev)
+
+        def step_T():
+            stT.y.copy_(y0T_dev)
+            _capi.check(_capi.lib.icnn_solve_batch_fused(netT._h, C.byref(fgT.c_gates), C.byref(cfT), C.byref(stT.c),
+                                                         fgT.ws.data_ptr(), stream))
+        for _ in range(3):
+            step_T()
+        torch.cuda.synchronize()
+        evT = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for a_, b_ in evT:
+            flush.fill_(1)
+            a_.record(); step_T(); b_.record()
+        torch.cuda.synchronize()
+        msT = sum(a_.elapsed_time(b_) for a_, b_ in evT) / len(evT)
+        itsT = int(np.sum(stT.nactive.cpu().numpy()[:cT["nIter"]] > 0))
+        extra_T = {"workload": "T: m=512 n_y=512 hidden=[1024,1024] batch=4096 nIter=10 (north-star target shape)",
+                   "value": cT["B"] * itsT / (msT * 1e-3), "unit": UNIT, "ms_per_step": msT, "iters_executed": itsT,
+                   "n_gpus": 1}
+        del stT, fgT, netT
     if world > 1:
         dist.barrier()
     line = None
@@ -357,7 +389,8 @@ def run_gpu(args):
         cpub = None
         if not args.no_cpu_baseline:
             cpub = cpu_baseline(args.workload, args.cpu_seconds)
-        launches_per_step = 2 + nIter * (2 * len(cfg["hidden"]) + 2)
+        tc_path = k1_name.startswith("tc_gemm")
+        launches_per_step = 2 + nIter * (2 * len(cfg["hidden"]) + (3 if tc_path else 2))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -372,7 +405,7 @@ def run_gpu(args):
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clk.summary(), "roofline": dominant,
             "kernels": {"K1_picnn_fg": roof_k1, "K2_bundle_step": roof_k2},
-            "cpu_baseline": cpub,
+            "cpu_baseline": cpub, "target_shape": extra_T,
         }
         print(json.dumps(line))
     if world > 1:
@@ -430,6 +463,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5", "T"])
     ap.add_argument("--solver", default="pc", choices=["pc", "newton"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-target-shape", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     try:

@@ -16,7 +16,11 @@
 //   gram pass   : warp owns 4x4 blocks of the k x k output ->  G diag(w) G^T         (shuffle reduce)
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <cstdlib>
+
+namespace cg = cooperative_groups;
 
 namespace icnn {
 
@@ -24,22 +28,74 @@ struct StepArgs {
   icnn_bundle_bufs b;
   icnn_bundle_cfg c;
   int t;
-  int npad;  // doubles reserved per n-vector in shared memory
+  int npad;  // doubles reserved per n-vector in shared memory (local column slice)
   int ld;    // leading dimension of the k x k matrices
+  int nloc;  // columns owned by one CTA (= n when the sample is not split over a cluster)
+  int gpitch;  // floats per resident G row in shared memory, 0 = rows are streamed from L2
 };
 
 constexpr int NKVEC = 20;  // k-vectors per group in shared memory
 
-__host__ __device__ inline size_t group_smem_doubles(int npad, int KS, int ld, int wps) {
-  // 3 n-vectors, 2 matrices, NKVEC k-vectors, reduction scratch, scalars
-  return (size_t)3 * npad + (size_t)2 * KS * ld + (size_t)NKVEC * KS + 4 * wps + 16;
+__host__ __device__ inline size_t xb_doubles(int KS, int ld) { return ((size_t)KS * ld + 2 * KS + 8 + 1) & ~(size_t)1; }
+
+__host__ __device__ inline size_t group_smem_doubles(int npad, int KS, int ld, int wps, int gpitch, int cs) {
+  // 3 n-vectors, 2 matrices, NKVEC k-vectors, reduction scratch, scalars,
+  // [cluster export buffer: M + 2 k-vectors + 8 scalars], [resident G rows: KS x gpitch floats]
+  size_t d = (size_t)3 * npad + (size_t)2 * KS * ld + (size_t)NKVEC * KS + 4 * wps + 16;
+  if (cs > 1) d += xb_doubles(KS, ld);
+  d += ((size_t)KS * gpitch + 1) / 2;
+  return (d + 1) & ~(size_t)1;
 }
 
-template <int WPS>
+// generic float load: bundle rows are either streamed from global memory or resident in shared memory
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+
+template <int WPS, int CS = 1>
 struct Grp {
   int tid, lane, warp, gid;
   double* red;  // [4*WPS]
+  double* xb;   // cluster export buffer (CS > 1): [KS*ld + 2*KS + 8]
   static constexpr int T = WPS * 32;
+
+  // ---- reductions over the whole sample = group, then (CS > 1) the CTAs of the cluster.  Every
+  // CTA combines the CS partials in rank order, so all CTAs hold bit-identical results and take
+  // identical branches.
+  __device__ __forceinline__ double cfold(double v, int op) const {
+    if (CS == 1) return v;
+    cg::cluster_group cl = cg::this_cluster();
+    if (tid == 0) xb[0] = v;
+    cl.sync();
+    double r = *cl.map_shared_rank(xb, 0);
+#pragma unroll
+    for (int q = 1; q < CS; ++q) {
+      const double o = *cl.map_shared_rank(xb, q);
+      r = (op == 0) ? r + o : (op == 1) ? fmin(r, o) : fmax(r, o);
+    }
+    cl.sync();
+    return r;
+  }
+  __device__ __forceinline__ double csum(double v) const { return cfold(sum(v), 0); }
+  __device__ __forceinline__ double cmin(double v) const { return cfold(min(v), 1); }
+  __device__ __forceinline__ double cmax(double v) const { return cfold(max(v), 2); }
+  // in-place cluster sum of up to three shared-memory segments (one exchange)
+  __device__ __forceinline__ void cvsum(double* p0, int l0, double* p1 = nullptr, int l1 = 0,
+                                        double* p2 = nullptr, int l2 = 0) const {
+    if (CS == 1) return;
+    cg::cluster_group cl = cg::this_cluster();
+    sync();
+    for (int i = tid; i < l0; i += T) xb[i] = p0[i];
+    for (int i = tid; i < l1; i += T) xb[l0 + i] = p1[i];
+    for (int i = tid; i < l2; i += T) xb[l0 + l1 + i] = p2[i];
+    cl.sync();
+    const int tot = l0 + l1 + l2;
+    for (int i = tid; i < tot; i += T) {
+      double r = 0.0;
+#pragma unroll
+      for (int q = 0; q < CS; ++q) r += *cl.map_shared_rank(xb + i, q);
+      if (i < l0) p0[i] = r; else if (i < l0 + l1) p1[i - l0] = r; else p2[i - l0 - l1] = r;
+    }
+    cl.sync();
+  }
 
   __device__ __forceinline__ void sync() const {
     if (WPS == 1) __syncwarp();
@@ -203,7 +259,7 @@ __device__ __forceinline__ void col_dots(const float* const* rowp, int k, int n,
     const double wj = w[j];
     float v[CHN];
 #pragma unroll
-    for (int c = 0; c < CHN; ++c) v[c] = (!PRED || cb + c * T + tid < n) ? __ldg(p + c * T) : 0.f;
+    for (int c = 0; c < CHN; ++c) v[c] = (!PRED || cb + c * T + tid < n) ? ldf(p + c * T) : 0.f;
 #pragma unroll
     for (int c = 0; c < CHN; ++c) acc[c] = fma((double)v[c], wj, acc[c]);
   }
@@ -243,8 +299,8 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 }
 
 // gram pass (fallback, any n): warp owns 4x4 blocks of M = G diag(w) G^T, lanes stride columns.
-template <int WPS>
-__device__ inline void gram_pass_simt(const Grp<WPS>& g, const float* const* rowp, int k, int n,
+template <int WPS, class G>
+__device__ inline void gram_pass_simt(const G& g, const float* const* rowp, int k, int n,
                                       const double* w, double* M, int ld) {
   const int kb = (k + 3) >> 2;
   const int nblk = kb * (kb + 1) / 2;
@@ -268,7 +324,7 @@ __device__ inline void gram_pass_simt(const Grp<WPS>& g, const float* const* row
       const double we = w[e];
       double vi[4], vj[4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) { vi[a] = (double)__ldg(ri[a] + e) * we; vj[a] = (double)__ldg(rj[a] + e); }
+      for (int a = 0; a < 4; ++a) { vi[a] = (double)ldf(ri[a] + e) * we; vj[a] = (double)ldf(rj[a] + e); }
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -292,8 +348,8 @@ __device__ inline void gram_pass_simt(const Grp<WPS>& g, const float* const* row
 // 8*blk + r, which are its A/B fragment elements for four consecutive k-steps (the four columns
 // of a k-step may be any four, as long as A, B and w agree).  Warp partials are then added into
 // M in warp order (deterministic).
-template <int WPS, int NA, int NB, bool TRI>
-__device__ inline void gram_sweep(const Grp<WPS>& g, const float* const* rowp, int k, int n,
+template <int WPS, int NA, int NB, bool TRI, class G>
+__device__ inline void gram_sweep(const G& g, const float* const* rowp, int k, int n,
                                   const double* w, double* M, int ld, int a0, int b0) {
   constexpr int NT = TRI ? NA * (NA + 1) / 2 : NA * NB;
   constexpr int NL = TRI ? NB : NA + NB;   // row blocks to load (TRI: A and B blocks coincide)
@@ -317,7 +373,7 @@ __device__ inline void gram_sweep(const Grp<WPS>& g, const float* const* rowp, i
     float4 v[NL];
 #pragma unroll
     for (int b = 0; b < NL; ++b)
-      v[b] = (cv && rok[b]) ? __ldg(reinterpret_cast<const float4*>(rp[b] + gi * 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[b] = (cv && rok[b]) ? *reinterpret_cast<const float4*>(rp[b] + gi * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
     double wv[4];
     if (cv) {
       const double2 w01 = *reinterpret_cast<const double2*>(w + col);
@@ -365,15 +421,15 @@ __device__ inline void gram_sweep(const Grp<WPS>& g, const float* const* rowp, i
   }
 }
 
-template <int WPS, int NB>
-__device__ inline void gram_rect_pair(const Grp<WPS>& g, const float* const* rowp, int k, int n,
+template <int WPS, int NB, class G>
+__device__ inline void gram_rect_pair(const G& g, const float* const* rowp, int k, int n,
                                       const double* w, double* M, int ld) {
   gram_sweep<WPS, 2, NB, false>(g, rowp, k, n, w, M, ld, 0, 4);
   gram_sweep<WPS, 2, NB, false>(g, rowp, k, n, w, M, ld, 2, 4);
 }
 
-template <int WPS>
-__device__ inline void gram_pass(const Grp<WPS>& g, const float* const* rowp, int k, int n,
+template <int WPS, class G>
+__device__ inline void gram_pass(const G& g, const float* const* rowp, int k, int n,
                                  const double* w, double* M, int ld) {
   if ((n & 3) != 0) { gram_pass_simt<WPS>(g, rowp, k, n, w, M, ld); g.sync(); return; }
   const int rb = (k + 7) >> 3;   // <= 8 (KS <= 64)
@@ -394,7 +450,11 @@ __device__ inline void gram_pass(const Grp<WPS>& g, const float* const* rowp, in
 
 // ---- the step kernel ----------------------------------------------------------------------
 
-template <int WPS, int MINB>
+// CS > 1: the sample is split over a thread-block cluster of CS CTAs by columns (WPS == 8); each
+// CTA keeps its column slice of the bundle rows RESIDENT in shared memory (A.gpitch > 0), runs
+// the column / row / Gram passes on its slice and exchanges the partial sums through distributed
+// shared memory; the k x k algebra is replicated in every CTA.
+template <int WPS, int MINB, int CS>
 __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
   const icnn_bundle_bufs& b = A.b;
   const icnn_bundle_cfg& cf = A.c;
@@ -402,17 +462,22 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
   extern __shared__ __align__(16) double smem_d[];
   constexpr int GPB = 8 / WPS;  // groups per block
   constexpr int T = WPS * 32;
-  Grp<WPS> g;
+  static_assert(CS == 1 || WPS == 8, "a cluster-split sample owns whole CTAs");
+  Grp<WPS, CS> g;
   g.tid = threadIdx.x % T;
   g.lane = threadIdx.x & 31;
   g.warp = g.tid >> 5;
   g.gid = threadIdx.x / T;
-  const int u = blockIdx.x * GPB + g.gid;
+  const int crank = (CS == 1) ? 0 : (int)cg::this_cluster().block_rank();
+  const int u = (CS == 1) ? blockIdx.x * GPB + g.gid : (int)(blockIdx.x / CS);
   if (u >= b.B) return;
   if (b.finished[u]) return;
 
-  const int n = b.n, KS = b.KS, ld = A.ld, npad = A.npad;
-  double* base = smem_d + (size_t)g.gid * group_smem_doubles(npad, KS, ld, WPS);
+  const int nglob = b.n, KS = b.KS, ld = A.ld, npad = A.npad;
+  const int c0 = crank * A.nloc;                       // first column of this CTA's slice
+  const int n = ::min(A.nloc, nglob - c0);             // columns of the slice ("n" below is LOCAL)
+  const bool lead = (crank == 0);                      // the CTA that writes per-sample scalars
+  double* base = smem_d + (size_t)g.gid * group_smem_doubles(npad, KS, ld, WPS, A.gpitch, CS);
   double* yv = base;            // n-vectors
   double* rv = yv + npad;
   double* dv = rv + npad;
@@ -442,19 +507,41 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
   g.red = kv + (size_t)NKVEC * KS;
   double* sc = g.red + 4 * WPS;  // 16 scalars
   int* isc = reinterpret_cast<int*>(sc + 12);  // 8 ints
+  g.xb = sc + 16;
+  float* Gs = reinterpret_cast<float*>(g.xb + (CS > 1 ? xb_doubles(KS, ld) : 0));
 
   const int k0 = b.count[u];
   const int k = k0 + 1;
   const int* permu = b.perm + (size_t)u * KS;
-  float* Gu = b.G + (size_t)u * KS * n;
+  float* Gu = b.G + (size_t)u * KS * nglob + c0;
   double* hu = b.h + (size_t)u * KS;
   double* lamu = b.lam + (size_t)u * KS;
   double* rsu = b.rsum + (size_t)u * KS;
   double* gramu = b.gram + (size_t)u * KS * KS;
-  double* yu = b.y + (size_t)u * n;
+  double* yu = b.y + (size_t)u * nglob + c0;
   const int slot_new = permu[k0];
 
-  for (int j = g.tid; j < k; j += T) rowp[j] = Gu + (size_t)permu[j] * n;
+  if (A.gpitch > 0) {
+    // stage this CTA's slice of the k active rows into shared memory: the only global read of the
+    // bundle in this launch (every pass below then runs out of shared memory)
+    const int gp = A.gpitch;
+    if ((n & 3) == 0 && (nglob & 3) == 0) {
+      const int n4 = n >> 2;
+      for (int idx = g.tid; idx < k * n4; idx += T) {
+        const int j = idx / n4, c = idx - j * n4;
+        reinterpret_cast<float4*>(Gs + (size_t)j * gp)[c] =
+            reinterpret_cast<const float4*>(Gu + (size_t)permu[j] * nglob)[c];
+      }
+    } else {
+      for (int idx = g.tid; idx < k * n; idx += T) {
+        const int j = idx / n, c = idx - j * n;
+        Gs[(size_t)j * gp + c] = Gu[(size_t)permu[j] * nglob + c];
+      }
+    }
+    for (int j = g.tid; j < k; j += T) rowp[j] = Gs + (size_t)j * gp;
+  } else {
+    for (int j = g.tid; j < k; j += T) rowp[j] = Gu + (size_t)permu[j] * nglob;
+  }
   if (g.tid == 0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) isc[i] = 0;
@@ -465,7 +552,7 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
   // ---- append: h = f - g.y ; row sum ; unweighted Gram row ; xs copy ; non-finite guard ------
   {
     double hs = 0.0, rs = 0.0, bad = 0.0;
-    double* ysrow = b.ys ? b.ys + ((size_t)u * KS + slot_new) * n : nullptr;
+    double* ysrow = b.ys ? b.ys + ((size_t)u * KS + slot_new) * nglob + c0 : nullptr;
     for (int e = g.tid; e < n; e += T) {
       const double ge = (double)gnew[e];
       const double ye = yu[e];
@@ -474,12 +561,12 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
       if (!isfinite(ge)) bad = 1.0;
       if (ysrow) ysrow[e] = ye;
     }
-    hs = g.sum(hs);
-    rs = g.sum(rs);
-    bad = g.max(bad);
+    hs = g.csum(hs);
+    rs = g.csum(rs);
+    bad = g.cmax(bad);
     const double fu = (double)b.f[u];
     if (bad > 0.0 || !isfinite(fu)) {
-      if (g.tid == 0) { b.status[u] = ICNN_ST_NONFINITE; b.finished[u] = 1; b.nIters[u] = A.t - 1; }
+      if (g.tid == 0 && lead) { b.status[u] = ICNN_ST_NONFINITE; b.finished[u] = 1; b.nIters[u] = A.t - 1; }
       return;
     }
     // Gram row of the new row against all active rows (row pass), plus exact-duplicate detection
@@ -488,15 +575,24 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
       double acc = 0.0;
       int diff = 0;
       for (int e = g.lane; e < n; e += 32) {
-        const float a = __ldg(rj + e), c = gnew[e];
+        const float a = ldf(rj + e), c = gnew[e];
         acc = fma((double)a, (double)c, acc);
         diff |= (a != c);
       }
       acc = Grp<WPS>::wsum(acc);
       diff = __any_sync(0xffffffffu, diff);
-      if (g.lane == 0) { tk[j] = acc; if (j < k0 && !diff) isc[0] = 1; }
+      if (g.lane == 0) { tk[j] = acc; ek[j] = diff ? 1.0 : 0.0; }
     }
-    if (g.tid == 0) { hu[slot_new] = fu - hs; rsu[slot_new] = rs; }
+    if (g.tid == 0 && lead) { hu[slot_new] = fu - hs; rsu[slot_new] = rs; }
+    g.sync();
+    g.cvsum(tk, k, ek, k);     // Gram row and per-row "differs somewhere" counts over all slices
+    if (g.tid == 0) {
+      int dup = 0;
+      for (int j = 0; j < k0; ++j) dup |= (ek[j] == 0.0);
+      isc[0] = dup;
+      sc[10] = fu - hs;        // h and row sum of the new row (identical in every CTA)
+      sc[11] = rs;
+    }
     g.sync();
   }
   // NOTE: control flow below is group-uniform: every decision is read from shared memory after
@@ -506,7 +602,7 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
     // ---- dependency test (stands in for np.linalg.matrix_rank, lib/bundle_entropy.py:219) ----
     // distance of the new row from the span of the active rows, computed explicitly (with one
     // step of iterative refinement in the gray zone), relative to the largest row norm.
-    if (k > n) dependent = true;
+    if (k > nglob) dependent = true;
     else if (k0 > 0) {
       if (g.warp == 0) {
         for (int i = g.lane; i < k0; i += 32)
@@ -537,7 +633,7 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
             rv[e] = r;
             p = fma(r, r, p);
           });
-          p = g.sum(p);
+          p = g.csum(p);
           if (p <= thr2) { dependent = true; break; }
           // clearly independent (relative distance > 1e-4), or already refined once
           if (rep == 1 || p > 1e-8 * maxdiag) break;
@@ -545,11 +641,12 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
           g.sync();
           for (int j = g.warp; j < k0; j += WPS) {
             double acc = 0.0;
-            for (int e = g.lane; e < n; e += 32) acc = fma((double)__ldg(rowp[j] + e), rv[e], acc);
+            for (int e = g.lane; e < n; e += 32) acc = fma((double)ldf(rowp[j] + e), rv[e], acc);
             acc = Grp<WPS>::wsum(acc);
             if (g.lane == 0) rk[j] = acc;
           }
           g.sync();
+          g.cvsum(rk, k0);
           if (g.warp == 0) { double* const r1[1] = {rk}; warp_chol_solve<1>(Lm, invd, k0, ld, r1, g.lane); }
           g.sync();
         }
@@ -559,16 +656,17 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
     }
     if (dependent) {
       // pop the row, mark finished, nIters = t-1 (lib/bundle_entropy.py:220-225); y unchanged
-      if (g.tid == 0) { b.status[u] = ICNN_ST_RANK_STOP; b.finished[u] = 1; b.nIters[u] = A.t - 1; }
+      if (g.tid == 0 && lead) { b.status[u] = ICNN_ST_RANK_STOP; b.finished[u] = 1; b.nIters[u] = A.t - 1; }
       return;
     }
   }
   // commit the Gram row
-  for (int j = g.tid; j < k; j += T) {
-    gramu[(size_t)slot_new * KS + permu[j]] = tk[j];
-    gramu[(size_t)permu[j] * KS + slot_new] = tk[j];
-  }
-  for (int j = g.tid; j < k; j += T) hk[j] = hu[permu[j]];  // permu[k0] == slot_new
+  if (lead)
+    for (int j = g.tid; j < k; j += T) {
+      gramu[(size_t)slot_new * KS + permu[j]] = tk[j];
+      gramu[(size_t)permu[j] * KS + slot_new] = tk[j];
+    }
+  for (int j = g.tid; j < k; j += T) hk[j] = (j == k0) ? sc[10] : hu[permu[j]];
   g.sync();
 
   int inner_its = 0;
@@ -586,31 +684,38 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
       double pr = 0.0;
       col_pass<T>(rowp, k, n, g.tid, zk, [&](int e, double a) {
         const double ye = yv[e];
-        const double r = log(ye) - log(1.0 - ye) + a;
+        const double r = log(ye / (1.0 - ye)) + a;   // = log y - log(1-y): one log + one division
         rv[e] = r;
         dv[e] = ye * (1.0 - ye);
         pr = fma(r, r, pr);
       });
-      pr = g.sum(pr);   // (contains the barrier that publishes rv / dv)
+      pr = g.sum(pr);   // local; (contains the barrier that publishes rv / dv)
       if (WPS == 1) __syncwarp();
       // row pass: rd = G y + h - t + s ; q = G D ry
       for (int j = g.warp; j < k; j += WPS) {
         const float* rj = rowp[j];
         double a1 = 0.0, a2 = 0.0;
         for (int e = g.lane; e < n; e += 32) {
-          const double ge = (double)__ldg(rj + e);
+          const double ge = (double)ldf(rj + e);
           a1 = fma(ge, yv[e], a1);
           a2 = fma(ge, dv[e] * rv[e], a2);
         }
         a1 = Grp<WPS>::wsum(a1);
         a2 = Grp<WPS>::wsum(a2);
-        if (g.lane == 0) { rdk[j] = a1 + hk[j] - sc[0] + sk[j]; qk[j] = a2; }
+        if (g.lane == 0) { rdk[j] = a1; qk[j] = a2; }   // column sums only; h - t + s is added below
       }
       // weighted Gram (independent of the row pass: reads only G and dv)
       gram_pass<WPS>(g, rowp, k, n, dv, M, ld);
       g.sync();
+      if (CS > 1) {   // one exchange: M, (G y, G D ry) and the squared residual norm
+        if (g.tid == 0) sc[11] = pr;
+        g.cvsum(M, k * ld, rdk, 2 * KS, sc + 11, 1);
+        pr = sc[11];
+      }
       if (g.warp == 0) {
         const int lane = g.lane;
+        for (int j = lane; j < k; j += 32) rdk[j] = ((rdk[j] + hk[j]) - sc[0]) + sk[j];   // rd = G y + h - t + s
+        __syncwarp();
         double zs = 0.0, dr = 0.0;
         for (int j = lane; j < k; j += 32) { zs += zk[j]; dr = fma(rdk[j], rdk[j], dr); }
         zs = Grp<1>::wsum(zs);
@@ -659,11 +764,13 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
         const double dy = -dv[e] * (rv[e] + a);
         rv[e] = dy;  // rv now holds dy_aff
         const double ye = yv[e];
-        if (dy < 0.0) st = fmin(st, -ye / dy);
-        if (dy > 0.0) st2 = fmin(st2, (1.0 - ye) / dy);
+        // get_step(y, dy) / get_step(1-y, -dy): one division serves whichever bound applies
+        const double ratio = (dy < 0.0 ? -ye : 1.0 - ye) / dy;
+        if (dy < 0.0) st = fmin(st, ratio);
+        if (dy > 0.0) st2 = fmin(st2, ratio);
       });
-      st = g.min(st);
-      st2 = g.min(st2);
+      st = g.cmin(st);
+      st2 = g.cmin(st2);
       st = fmin(st > 1e299 ? 1.0 : st, st2 > 1e299 ? 1.0 : st2);
       if (g.warp == 0) {
         const int lane = g.lane;
@@ -709,11 +816,13 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
         const double dy = rv[e] - dv[e] * a;
         rv[e] = dy;
         const double ye = yv[e];
-        if (dy < 0.0) st = fmin(st, -ye / dy);
-        if (dy > 0.0) st2 = fmin(st2, (1.0 - ye) / dy);
+        // get_step(y, dy) / get_step(1-y, -dy): one division serves whichever bound applies
+        const double ratio = (dy < 0.0 ? -ye : 1.0 - ye) / dy;
+        if (dy < 0.0) st = fmin(st, ratio);
+        if (dy > 0.0) st2 = fmin(st2, ratio);
       });
-      st = g.min(st);
-      st2 = g.min(st2);
+      st = g.cmin(st);
+      st2 = g.cmin(st2);
       st = fmin(st > 1e299 ? 1.0 : st, st2 > 1e299 ? 1.0 : st2);
       if (g.warp == 0) {
         const int lane = g.lane;
@@ -739,7 +848,7 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
       if (g.tid == 0) zk[0] = 1.0;  // lam = [1]  (:166-168)
       g.sync();
     } else {
-      for (int j = g.tid; j < k; j += T) { zk[j] = 1.0 / k; ck[j] = rsu[permu[j]] + hk[j]; ek[j] = 1.0; }
+      for (int j = g.tid; j < k; j += T) { zk[j] = 1.0 / k; ck[j] = ((j == k0) ? sc[11] : rsu[permu[j]]) + hk[j]; ek[j] = 1.0; }
       g.sync();
       bool done = false;
       for (int it = 0; it < maxit && !done; ++it) {
@@ -752,17 +861,20 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
           dv[e] = ze * (1.0 - ze);
           fs += softplus_d(a);
         });
-        fs = g.sum(fs);
+        fs = g.csum(fs);
         if (WPS == 1) __syncwarp();
         // row pass: grad = -c + G z
         for (int j = g.warp; j < k; j += WPS) {
           const float* rj = rowp[j];
           double acc = 0.0;
-          for (int e = g.lane; e < n; e += 32) acc = fma((double)__ldg(rj + e), yv[e], acc);
+          for (int e = g.lane; e < n; e += 32) acc = fma((double)ldf(rj + e), yv[e], acc);
           acc = Grp<WPS>::wsum(acc);
-          if (g.lane == 0) gk[j] = acc - ck[j];
+          if (g.lane == 0) gk[j] = acc;   // G z (column sums only); -c is added below
         }
         gram_pass<WPS>(g, rowp, k, n, dv, M, ld);
+        g.sync();
+        g.cvsum(M, k * ld, gk, k);
+        for (int j = g.tid; j < k; j += T) gk[j] -= ck[j];   // grad = -c + G z
         g.sync();
         if (g.warp == 0) {
           const int lane = g.lane;
@@ -869,7 +981,7 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
             if (cf.line_search) {
               double fs2 = 0.0;
               col_pass<T>(rowp, k, n, g.tid, lnk, [&](int e, double a) { fs2 += softplus_d(a); });
-              fs2 = g.sum(fs2);
+              fs2 = g.csum(fs2);
               double cl = 0.0;
               for (int j = 0; j < k; ++j) cl = fma(ck[j], lnk[j], cl);
               const double Fn = fs2 - cl;
@@ -905,11 +1017,11 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
     if (!isfinite(ye)) bad = 1.0;
     maxdiff = fmax(maxdiff, fabs(yu[e] - ye));
     yu[e] = ye;
-    b.y32[(size_t)u * n + e] = (float)ye;
+    b.y32[(size_t)u * nglob + c0 + e] = (float)ye;
   }
-  if (rl) maxdiff = g.max(maxdiff);
-  bad = g.max(bad);
-  if (g.tid == 0) {
+  if (rl) maxdiff = g.cmax(maxdiff);
+  bad = g.cmax(bad);
+  if (g.tid == 0 && lead) {
     // prune (keep lam > thr), rebuild perm: kept slots, then dropped, then the old free tail
     int nk = 0, nd = 0;
     int dropped[64], oldp[64];
@@ -960,39 +1072,93 @@ __global__ void put_fg_kernel(icnn_bundle_bufs b, const float* f, const float* g
   if (threadIdx.x == 0) b.f[u] = f[u];
 }
 
-// warps per sample: enough columns per thread to amortise the per-row shared-memory reads,
-// few enough warps that the warp-0 dense algebra does not idle most of the group
-static int pick_wps(int n) {
-  const char* v = getenv("ICNN_K2_WPS");
-  if (v) { const int w = atoi(v); if (w == 1 || w == 2 || w == 4 || w == 8) return w; }
-  return n <= 128 ? 1 : (n <= 512 ? 2 : (n <= 1024 ? 4 : 8));
+// Launch configuration: warps per sample (WPS), cluster size over columns (CS) and whether the
+// sample's rows are kept resident in shared memory.
+//   n <= 128: 1 warp / sample, <= 512: 2, <= 1024: 4, else 8 (one CTA per column slice);
+//   resident rows whenever KS x slice fits next to the work vectors; the sample is split over
+//   CS = 2/4/8 CTAs of a cluster when one CTA cannot hold it (or to get two CTAs per SM).
+struct K2Config { int wps, cs, nloc, gpitch, npad, ld; size_t smem; };
+
+static bool k2_fits(const icnn_bundle_bufs* b, int wps, int cs, bool resident, size_t limit, K2Config* out) {
+  K2Config c;
+  c.wps = wps; c.cs = cs;
+  c.nloc = (cs == 1) ? b->n : (((b->n + cs - 1) / cs + 3) & ~3);
+  if (cs > 1 && (long long)c.nloc * (cs - 1) >= b->n) return false;      // an empty slice
+  c.npad = (c.nloc + 3) & ~3;
+  c.ld = b->KS | 1;
+  c.gpitch = 0;
+  if (resident) { const int p4 = (c.nloc + 3) & ~3; c.gpitch = p4 + ((16 - (p4 & 31)) & 31); }   // = 16 mod 32 floats
+  c.smem = sizeof(double) * group_smem_doubles(c.npad, b->KS, c.ld, wps, c.gpitch, cs) * (8 / wps);
+  if (c.smem > limit) return false;
+  *out = c;
+  return true;
+}
+
+static int pick_k2(const icnn_bundle_bufs* b, K2Config* out) {
+  const int n = b->n;
+  int wps = n <= 128 ? 1 : (n <= 512 ? 2 : (n <= 1024 ? 4 : 8));
+  if (const char* v = getenv("ICNN_K2_WPS")) { const int w = atoi(v); if (w == 1 || w == 2 || w == 4 || w == 8) wps = w; }
+  int want_cs = 0;
+  if (const char* v = getenv("ICNN_K2_CS")) want_cs = atoi(v);
+  const char* rv = getenv("ICNN_K2_RESIDENT");
+  const bool allow_res = !(rv && rv[0] == '0');
+  const size_t big = 200 * 1024, half = 110 * 1024;
+  if (want_cs == 1 || want_cs == 2 || want_cs == 4 || want_cs == 8) {
+    if (k2_fits(b, want_cs > 1 ? 8 : wps, want_cs, allow_res, big, out)) return ICNN_OK;
+    if (want_cs == 1 && k2_fits(b, wps, 1, false, 227 * 1024, out)) return ICNN_OK;
+    set_error("bundle_step: ICNN_K2_CS=%d does not fit (n=%d, KS=%d)", want_cs, n, b->KS);
+    return ICNN_E_UNSUPPORTED;
+  }
+  if (allow_res) {
+    if (k2_fits(b, wps, 1, true, half, out)) return ICNN_OK;                 // resident, >= 2 CTAs / SM
+    if (wps == 8 || n > 1024) {
+      for (int cs = 2; cs <= 8; cs *= 2) if (k2_fits(b, 8, cs, true, half, out)) return ICNN_OK;
+      if (k2_fits(b, 8, 1, true, big, out)) return ICNN_OK;
+      for (int cs = 2; cs <= 8; cs *= 2) if (k2_fits(b, 8, cs, true, big, out)) return ICNN_OK;
+    } else if (k2_fits(b, wps, 1, true, big, out)) return ICNN_OK;
+  }
+  if (k2_fits(b, wps, 1, false, 227 * 1024, out)) return ICNN_OK;               // rows streamed from L2
+  set_error("bundle_step: shared memory does not fit (n=%d, KS=%d)", n, b->KS);
+  return ICNN_E_UNSUPPORTED;
+}
+
+template <int WPS, int CS>
+static cudaError_t launch_k2(const StepArgs& a, const K2Config& c, int B, cudaStream_t st) {
+  // 3 CTAs / SM (80 registers) when the shared-memory footprint allows it, else the 128-register build
+  const bool three = c.smem * 3 <= 225 * 1024;
+  void (*kern)(StepArgs) = three ? bundle_step_kernel<WPS, 3, CS> : bundle_step_kernel<WPS, 2, CS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(CS == 1 ? cdiv(B, 8 / WPS) : B * CS));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = c.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 int bundle_step_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int t, cudaStream_t st) {
+  if (b->KS > 64) { set_error("bundle_step: KS=%d > 64 unsupported", b->KS); return ICNN_E_UNSUPPORTED; }
+  K2Config c;
+  int rc = pick_k2(b, &c);
+  if (rc) return rc;
   StepArgs a;
   a.b = *b; a.c = *cfg; a.t = t;
-  a.npad = (b->n + 3) & ~3;
-  a.ld = b->KS | 1;
-  const int wps = pick_wps(b->n);
-  const size_t smem = sizeof(double) * group_smem_doubles(a.npad, b->KS, a.ld, wps) * (8 / wps);
-  if (smem > 227 * 1024) {
-    set_error("bundle_step: shared memory %zu B exceeds 227 KB (n=%d, KS=%d)", smem, b->n, b->KS);
-    return ICNN_E_UNSUPPORTED;
-  }
-  if (b->KS > 64) { set_error("bundle_step: KS=%d > 64 unsupported", b->KS); return ICNN_E_UNSUPPORTED; }
+  a.npad = c.npad; a.ld = c.ld; a.nloc = c.nloc; a.gpitch = c.gpitch;
   cudaError_t e;
-  // ICNN_K2_MINB=2 selects the 128-register build (2 CTAs/SM); default 3 CTAs/SM (80 registers)
-  static const int minb = [] { const char* v = getenv("ICNN_K2_MINB"); return (v && v[0] == '2') ? 2 : 3; }();
-  void (*kern)(StepArgs) = nullptr;
-  if (wps == 1) kern = (minb == 2) ? bundle_step_kernel<1, 2> : bundle_step_kernel<1, 3>;
-  else if (wps == 2) kern = (minb == 2) ? bundle_step_kernel<2, 2> : bundle_step_kernel<2, 3>;
-  else if (wps == 4) kern = (minb == 2) ? bundle_step_kernel<4, 2> : bundle_step_kernel<4, 3>;
-  else kern = (minb == 2) ? bundle_step_kernel<8, 2> : bundle_step_kernel<8, 3>;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
-  kern<<<cdiv(b->B, 8 / wps), 256, smem, st>>>(a);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) { set_error("bundle_step launch: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
+  if (c.cs == 8) e = launch_k2<8, 8>(a, c, b->B, st);
+  else if (c.cs == 4) e = launch_k2<8, 4>(a, c, b->B, st);
+  else if (c.cs == 2) e = launch_k2<8, 2>(a, c, b->B, st);
+  else if (c.wps == 1) e = launch_k2<1, 1>(a, c, b->B, st);
+  else if (c.wps == 2) e = launch_k2<2, 1>(a, c, b->B, st);
+  else if (c.wps == 4) e = launch_k2<4, 1>(a, c, b->B, st);
+  else e = launch_k2<8, 1>(a, c, b->B, st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("bundle_step launch (wps=%d cs=%d smem=%zu): %s", c.wps, c.cs, c.smem, cudaGetErrorString(e)); return ICNN_E_CUDA; }
   return ICNN_OK;
 }
 
