@@ -1100,8 +1100,12 @@ static int pick_k2(const icnn_bundle_bufs* b, K2Config* out) {
   if (const char* v = getenv("ICNN_K2_WPS")) { const int w = atoi(v); if (w == 1 || w == 2 || w == 4 || w == 8) wps = w; }
   int want_cs = 0;
   if (const char* v = getenv("ICNN_K2_CS")) want_cs = atoi(v);
+  // Resident rows / cluster split are OFF by default: measured on B200 (round 1) they lose to
+  // streaming the rows from L2 on every configuration (C2 53.7 vs 20.4 ms, T 17.7 vs 9.4 ms,
+  // C5/512 773 vs 188 ms per solveBatch) -- the per-sample solve is a latency-bound FP64 chain, and
+  // what hides it is the number of samples in flight per SM, which residency divides by 3-5.
   const char* rv = getenv("ICNN_K2_RESIDENT");
-  const bool allow_res = !(rv && rv[0] == '0');
+  const bool allow_res = (rv && rv[0] == '1');
   const size_t big = 200 * 1024, half = 110 * 1024;
   if (want_cs == 1 || want_cs == 2 || want_cs == 4 || want_cs == 8) {
     if (k2_fits(b, want_cs > 1 ? 8 : wps, want_cs, allow_res, big, out)) return ICNN_OK;

@@ -268,3 +268,24 @@ def test_early_exit_when_all_finished():
     o = bundle_np.solve_batch(picnn_np.make_fg(p, x), y0.copy(), nIter=40)
     assert na[0] == 16 and na[-1] == 0 and max(r[5]) < 39
     assert rowdiff(r[0], o[0]).max() < 1e-4
+
+
+@pytest.mark.parametrize("name,B,nIter,env", [("C2", 5, 12, {"ICNN_K2_RESIDENT": "1"}),
+                                              ("C2", 5, 12, {"ICNN_K2_RESIDENT": "1", "ICNN_K2_CS": "2"}),
+                                              ("T", 20, 10, {"ICNN_K2_RESIDENT": "1"}),
+                                              ("C3", 20, 10, {"ICNN_K2_RESIDENT": "1"}),
+                                              ("C5", 3, 12, {"ICNN_K2_RESIDENT": "1", "ICNN_K2_CS": "8"})])
+def test_resident_cluster_variant_matches_streaming(name, B, nIter, env, monkeypatch):
+    """The optional K2 variant (rows resident in shared memory, sample split over a thread-block
+    cluster with DSMEM exchanges) computes the same thing as the default streaming kernel.  The
+    launch configuration is read from the environment at every launch."""
+    from icnn_b200 import bundle_entropy as be
+    p, x, y0 = synth.make_inputs(name, B=B)
+    fg = r32(picnn_np.make_fg(p, x))
+    ref = be.solveBatch(fg, y0.copy(), nIter=nIter)
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
+    alt = be.solveBatch(fg, y0.copy(), nIter=nIter)
+    same = (lens(ref[1]) == lens(alt[1])) & (np.array(ref[5]) == np.array(alt[5]))
+    assert same.mean() >= 0.8
+    assert rowdiff(ref[0], alt[0])[same].max() < 1e-9
