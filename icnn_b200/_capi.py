@@ -25,7 +25,7 @@ SYMBOLS = [
     "icnn_last_error", "icnn_abi_version", "icnn_device_count",
     "icnn_picnn_create", "icnn_picnn_destroy", "icnn_picnn_workspace_bytes", "icnn_picnn_fg",
     "icnn_bundle_init", "icnn_bundle_put_fg", "icnn_bundle_step",
-    "icnn_solve_batch_fused", "icnn_gd_solve", "icnn_tc_gemm_selftest",
+    "icnn_solve_batch_fused", "icnn_gd_solve", "icnn_tc_gemm_selftest", "icnn_argmin_grad",
 ]
 
 _fpp = C.POINTER(C.c_void_p)
@@ -85,6 +85,8 @@ def _load():
                                   C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     lib.icnn_tc_gemm_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_void_p]
+    lib.icnn_argmin_grad.argtypes = [C.POINTER(BundleBufs), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
     for name in SYMBOLS:
         getattr(lib, name)  # AttributeError if the .so does not export it
     if lib.icnn_abi_version() != ABI_VERSION:

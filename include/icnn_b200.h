@@ -141,6 +141,15 @@ int icnn_bundle_put_fg(const icnn_bundle_bufs* b, const float* f, const float* g
  * y update, prune.  f and the new row must already be in place. */
 int icnn_bundle_step(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int32_t t, void* stream);
 
+/* ---- K3: argmin differentiation ------------------------------------ */
+/* replaces: crossEntrGrad (multi-label-cls/icnn_ebundle.py:390-417, loss = 1) / mseGrad
+ * (completion/icnn_ebundle.py:493-522, loss = 0) and the (v, c) assembly of train_step_fd
+ * (multi-label-cls/icnn_ebundle.py:296-314), on the final bundle state of a solve.
+ * trueY [B, n] f64; outputs cy [B, n], clam [B, KS] (list order), ct [B], optional
+ * V [B, KS, n] with V[u, i] = lam_i * cy + clam_i * (y* - ys_i)  (all device, f64). */
+int icnn_argmin_grad(const icnn_bundle_bufs* b, int32_t loss, const double* trueY, double* cy,
+                     double* clam, double* ct, double* V, void* stream);
+
 /* ---- fused loops --------------------------------------------------------------------------- */
 /* replaces: solveBatch end to end (lib/bundle_entropy.py:192-242) with fg = the PICNN handle:
  * nIter x (K1, K2) enqueued back to back on the stream, no host round trip; iterations after

@@ -1,0 +1,66 @@
+"""K3 parity: argmin differentiation (crossEntrGrad / mseGrad + the train_step_fd assembly) on the
+GPU against the numpy restatement and the golden vectors produced by the reference's own function
+bodies (oracle/gen_golden_grad.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import argmin_grad_np, bundle_np, picnn_np, synth
+
+pytestmark = pytest.mark.gpu
+np.seterr(all="ignore")
+
+
+def r32(fg):
+    def w(y):
+        f, g = fg(y)
+        return f.astype(np.float32).astype(np.float64), g.astype(np.float32).astype(np.float64)
+    return w
+
+
+@pytest.mark.parametrize("name,B,nIter", [("C1", 32, 5), ("C3", 24, 10), ("T", 10, 8), ("C2", 4, 12)])
+@pytest.mark.parametrize("loss", ["xent", "mse"])
+def test_argmin_grad_matches_oracle(name, B, nIter, loss):
+    from icnn_b200 import argmin_grad, bundle_entropy as be
+    p, x, y0 = synth.make_inputs(name, B=B)
+    fg = r32(picnn_np.make_fg(p, x))
+    out = be.solveBatch(fg, y0.copy(), nIter=nIter, return_state=True)
+    yN, G, h, lam, ys, nIters, st = out
+    trueY = (np.random.RandomState(17).uniform(size=yN.shape) < 0.3).astype(np.float64)
+    cy, clam, ct, (fd_ys, fd_vs, fd_cs) = argmin_grad.argmin_grad(st, trueY, loss=loss)
+    # oracle on the GPU's own bundle state (isolates K3 from trajectory differences)
+    Gl = [np.array(G[u], dtype=np.float64) for u in range(B)]
+    scale = 0.0
+    for u in range(B):
+        ocy, oclam, oct = argmin_grad_np.argmin_grad(yN[u], trueY[u], Gl[u], loss)
+        tol = 1e-8 * max(1.0, np.abs(ocy).max(), np.abs(oclam).max())
+        np.testing.assert_allclose(cy[u], ocy, atol=tol)
+        np.testing.assert_allclose(clam[u], oclam, atol=tol)
+        np.testing.assert_allclose(ct[u], oct[0], atol=tol)
+        scale = max(scale, np.abs(ocy).max())
+    oys, ovs, ocs = argmin_grad_np.train_step_pairs(yN, trueY, Gl, [list(ys[u]) for u in range(B)],
+                                                    [lam[u] for u in range(B)], loss)
+    assert fd_vs.shape == ovs.shape and fd_ys.shape == oys.shape
+    np.testing.assert_allclose(fd_ys, oys, atol=0)
+    np.testing.assert_allclose(fd_vs, ovs, atol=1e-8 * max(1.0, scale))
+    np.testing.assert_allclose(fd_cs, ocs, atol=1e-8 * max(1.0, np.abs(ocs).max()))
+
+
+@pytest.mark.parametrize("tag,name,B,nIter", [("c1", "C1", 32, 5), ("c3", "C3", 12, 10)])
+def test_argmin_grad_against_reference_golden(tag, name, B, nIter, golden_dir):
+    """End to end: GPU solve (float64 oracle fg) + GPU K3 vs the reference's solveBatch + the
+    reference's crossEntrGrad / mseGrad bodies.  The bundle states differ at float32-rounding level,
+    so the tolerance is the solve's (1e-4 relative), not K3's."""
+    from icnn_b200 import argmin_grad, bundle_entropy as be
+    gold = np.load(os.path.join(golden_dir, "argmin_grad.npz"))
+    p, x, y0 = synth.make_inputs(name, B=B)
+    out = be.solveBatch(picnn_np.make_fg(p, x), y0.copy(), nIter=nIter, return_state=True)
+    st = out[-1]
+    same = np.array([len(g) for g in out[1]]) == gold[tag + "_counts"]
+    assert same.mean() >= 0.8
+    for loss in ("xent", "mse"):
+        cy, clam, ct = argmin_grad.argmin_grad(st, gold[tag + "_trueY"], loss=loss, assemble=False)
+        ref = gold["%s_%s_cy" % (tag, loss)]
+        err = np.abs(cy - ref).max(axis=1)[same] / max(1.0, np.abs(ref).max())
+        assert np.median(err) < 1e-5 and np.mean(err < 1e-3) >= 0.9, err
