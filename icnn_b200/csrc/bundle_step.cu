@@ -253,7 +253,7 @@ __device__ __forceinline__ void col_dots(const float* const* rowp, int k, int n,
 #pragma unroll
   for (int c = 0; c < CHN; ++c) acc[c] = 0.0;
   // several rows in flight per thread: the row loads are L2-latency bound
-#pragma unroll (CHN >= 8 ? 2 : (CHN >= 4 ? 6 : 8))
+#pragma unroll (CHN >= 8 ? 2 : 4)
   for (int j = 0; j < k; ++j) {
     const float* p = rowp[j] + cb + tid;
     const double wj = w[j];
@@ -283,8 +283,8 @@ template <int T, class F>
 __device__ __forceinline__ void col_pass(const float* const* rowp, int k, int n, int tid,
                                          const double* w, F&& f) {
   int cb = 0;
-  // 4 columns x 6 rows = 24 independent loads in flight per thread (the rows stream from L2)
-  for (; cb + 4 * T <= n; cb += 4 * T) col_chunk<T, 4, false>(rowp, k, n, cb, tid, w, f);
+  for (; cb + 8 * T <= n; cb += 8 * T) col_chunk<T, 8, false>(rowp, k, n, cb, tid, w, f);
+  if (cb + 4 * T <= n) { col_chunk<T, 4, false>(rowp, k, n, cb, tid, w, f); cb += 4 * T; }
   if (cb + 2 * T <= n) { col_chunk<T, 2, false>(rowp, k, n, cb, tid, w, f); cb += 2 * T; }
   if (cb + T <= n) { col_chunk<T, 1, false>(rowp, k, n, cb, tid, w, f); cb += T; }
   if (cb < n) col_chunk<T, 1, true>(rowp, k, n, cb, tid, w, f);
@@ -367,7 +367,6 @@ __device__ inline void gram_sweep(const G& g, const float* const* rowp, int k, i
     rp[b] = rowp[rok[b] ? row : k - 1] + 4 * q;
   }
   const int ngrp = (n + 15) >> 4;
-#pragma unroll 2
   for (int gi = g.warp; gi < ngrp; gi += WPS) {
     const int col = gi * 16 + 4 * q;
     const bool cv = col < n;  // n % 4 == 0: the whole float4 is in or out
@@ -575,7 +574,6 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
       const float* rj = rowp[j];
       double acc = 0.0;
       int diff = 0;
-#pragma unroll 8
       for (int e = g.lane; e < n; e += 32) {
         const float a = ldf(rj + e), c = gnew[e];
         acc = fma((double)a, (double)c, acc);
@@ -697,7 +695,6 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
       for (int j = g.warp; j < k; j += WPS) {
         const float* rj = rowp[j];
         double a1 = 0.0, a2 = 0.0;
-#pragma unroll 8
         for (int e = g.lane; e < n; e += 32) {
           const double ge = (double)ldf(rj + e);
           a1 = fma(ge, yv[e], a1);

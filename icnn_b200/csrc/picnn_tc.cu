@@ -22,6 +22,9 @@
 
 #include <cuda.h>
 
+#include <cstdlib>
+#include <cstring>
+
 namespace icnn {
 
 // ---------------------------------------------------------------------------------------------
@@ -138,9 +141,9 @@ struct TcArgs {
   const int* skip_if_zero;
 };
 
-template <int BN>
+template <int BN, int NST_>
 struct TcSmem {
-  static constexpr int NST = (BN == 128) ? 3 : 4;
+  static constexpr int NST = NST_;
   static constexpr int A_BYTES = TC_BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -148,12 +151,15 @@ struct TcSmem {
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // + alignment slack
 };
 
-template <int BN>
-__global__ void __launch_bounds__(192, 1)
+// <128,3>: one CTA / SM (198 KB);  <64,4>: one CTA / SM, deeper ring for small grids;
+// <64,2>: two CTAs / SM (98 KB each, 2 x 256 TMEM columns) so that one CTA's epilogue overlaps
+// the other's main loop.
+template <int BN, int NST_>
+__global__ void __launch_bounds__(192, (BN == 64 && NST_ == 2) ? 2 : 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, TcArgs a) {
   if (a.skip_if_zero != nullptr && *a.skip_if_zero == 0) return;
-  using S = TcSmem<BN>;
+  using S = TcSmem<BN, NST_>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
@@ -426,29 +432,40 @@ static int make_tmap(CUtensorMap* tm, const float* base, long long rows, long lo
   return ICNN_OK;
 }
 
+template <int BN, int NST_>
+static cudaError_t launch_tc_variant(const CUtensorMap& tAh, const CUtensorMap& tAl, const CUtensorMap& tBh,
+                                     const CUtensorMap& tBl, const TcArgs& a, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, NST_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TcSmem<BN, NST_>::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  dim3 grid(cdiv(a.N, BN), cdiv(a.M, TC_BM));
+  tc_gemm_kernel<BN, NST_><<<grid, 192, TcSmem<BN, NST_>::TOTAL, st>>>(tAh, tAl, tBh, tBl, a);
+  return cudaGetLastError();
+}
+
 static int launch_tc_gemm(const float* Ah, const float* Al, long long lda, const float* Bh, const float* Bl, long long ldb,
                           TcArgs a, cudaStream_t st) {
   const int gy = cdiv(a.M, TC_BM);
-  const bool wide = (cdiv(a.N, 128) * gy >= 148) && (a.N >= 128);
-  const int BN = wide ? 128 : 64;
+  // tile choice: 128-wide tiles when they still cover the chip, else 64-wide; 64-wide with two
+  // CTAs per SM once there are >= 2 tiles per SM.  ICNN_TC_CFG=128|64x4|64x2 forces one.
+  int cfg = (cdiv(a.N, 128) * gy >= 148 && a.N >= 128) ? 0 : ((cdiv(a.N, 64) * gy >= 296) ? 2 : 1);
+  if (const char* v = getenv("ICNN_TC_CFG")) {
+    if (!strcmp(v, "128")) cfg = 0; else if (!strcmp(v, "64x4")) cfg = 1; else if (!strcmp(v, "64x2")) cfg = 2;
+  }
+  const int BN = cfg == 0 ? 128 : 64;
   CUtensorMap tAh, tAl, tBh, tBl;
   int rc;
   if ((rc = make_tmap(&tAh, Ah, a.M, a.K, lda, TC_BM))) return rc;
   if ((rc = make_tmap(&tAl, Al, a.M, a.K, lda, TC_BM))) return rc;
   if ((rc = make_tmap(&tBh, Bh, a.N, a.K, ldb, BN))) return rc;
   if ((rc = make_tmap(&tBl, Bl, a.N, a.K, ldb, BN))) return rc;
-  dim3 grid(cdiv(a.N, BN), gy);
-  cudaError_t e;
-  if (BN == 128) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128>::TOTAL); attr = true; }
-    tc_gemm_kernel<128><<<grid, 192, TcSmem<128>::TOTAL, st>>>(tAh, tAl, tBh, tBl, a);
-  } else {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(tc_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64>::TOTAL); attr = true; }
-    tc_gemm_kernel<64><<<grid, 192, TcSmem<64>::TOTAL, st>>>(tAh, tAl, tBh, tBl, a);
-  }
-  e = cudaGetLastError();
+  cudaError_t e = cfg == 0 ? launch_tc_variant<128, 3>(tAh, tAl, tBh, tBl, a, st)
+                : cfg == 1 ? launch_tc_variant<64, 4>(tAh, tAl, tBh, tBl, a, st)
+                           : launch_tc_variant<64, 2>(tAh, tAl, tBh, tBl, a, st);
   if (e != cudaSuccess) { set_error("tc_gemm launch: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
   return ICNN_OK;
 }
