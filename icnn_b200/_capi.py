@@ -26,6 +26,7 @@ SYMBOLS = [
     "icnn_picnn_create", "icnn_picnn_destroy", "icnn_picnn_workspace_bytes", "icnn_picnn_fg",
     "icnn_bundle_init", "icnn_bundle_put_fg", "icnn_bundle_step",
     "icnn_solve_batch_fused", "icnn_gd_solve", "icnn_tc_gemm_selftest", "icnn_argmin_grad",
+    "icnn_picnn_set_xpath", "icnn_picnn_gates_workspace_bytes", "icnn_picnn_gates",
 ]
 
 _fpp = C.POINTER(C.c_void_p)
@@ -85,6 +86,10 @@ def _load():
                                   C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     lib.icnn_tc_gemm_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_void_p]
+    lib.icnn_picnn_set_xpath.argtypes = [C.c_void_p, C.c_int32] + [_fpp] * 8 + [C.c_void_p]
+    lib.icnn_picnn_gates_workspace_bytes.argtypes = [C.c_void_p, C.c_int32]
+    lib.icnn_picnn_gates_workspace_bytes.restype = C.c_size_t
+    lib.icnn_picnn_gates.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, _fpp, _fpp, _fpp, C.c_void_p, C.c_void_p]
     lib.icnn_argmin_grad.argtypes = [C.POINTER(BundleBufs), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
     for name in SYMBOLS:

@@ -47,6 +47,11 @@ struct icnn_picnn {
   float* Wb_hi[ICNN_MAX_LAYERS]; float* Wb_lo[ICNN_MAX_LAYERS];
   float* Wf_hi[ICNN_MAX_LAYERS]; float* Wf_lo[ICNN_MAX_LAYERS];
   bool use_tc;
+  // x-path (gate precompute) weights: per source s = 0..L the N-concatenated, transposed, hi/lo-split
+  // [Wu_s | Wzu_s | Wyu_s | Wzx_s] and the matching bias vector
+  int m; bool has_xpath;
+  float* Xw_hi[ICNN_MAX_LAYERS + 1]; float* Xw_lo[ICNN_MAX_LAYERS + 1]; float* Xbias[ICNN_MAX_LAYERS + 1];
+  int xN[ICNN_MAX_LAYERS + 1]; int xK[ICNN_MAX_LAYERS + 1];
   int width(int i) const { return i < L ? hidden[i] : 1; }
   int prev(int i) const { return i == 0 ? 0 : hidden[i - 1]; }
 };

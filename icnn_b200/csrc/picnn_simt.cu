@@ -315,6 +315,7 @@ void out_layer_launch(const icnn_picnn* h, const icnn_gates* gt, const float* Zl
 bool picnn_tc_supported(const icnn_picnn* h);
 int picnn_tc_prepare_weights(icnn_picnn* h, cudaStream_t st);
 void picnn_tc_free_weights(icnn_picnn* h);
+void picnn_xpath_free(icnn_picnn* h);
 size_t picnn_tc_ws_floats(const icnn_picnn* h, int B, size_t* aoff, size_t* doff);
 int picnn_fg_tc(const icnn_picnn* h, const icnn_gates* gt, const float* y32, float* f, float* g,
                 long long g_row_stride, const int* perm, const int* count, int KS, void* workspace,
@@ -388,6 +389,8 @@ extern "C" int icnn_picnn_create(const icnn_picnn_desc* d, icnn_picnn_t** out, v
   for (int i = 0; i <= d->L; ++i) h->Wcat[i] = nullptr;
   for (int i = 0; i < ICNN_MAX_LAYERS; ++i) h->Wb_hi[i] = h->Wb_lo[i] = h->Wf_hi[i] = h->Wf_lo[i] = nullptr;
   h->use_tc = false;
+  h->m = 0; h->has_xpath = false;
+  for (int i = 0; i <= ICNN_MAX_LAYERS; ++i) h->Xw_hi[i] = h->Xw_lo[i] = h->Xbias[i] = nullptr;
   for (int i = 0; i <= d->L; ++i) {
     const long long si = h->width(i), sp = h->prev(i);
     const long long ntop = sp * si, nbot = (long long)h->n * si;
@@ -419,6 +422,7 @@ extern "C" int icnn_picnn_destroy(icnn_picnn_t* h) {
   for (int i = 0; i <= h->L && i <= ICNN_MAX_LAYERS; ++i)
     if (h->Wcat[i]) cudaFree(h->Wcat[i]);
   picnn_tc_free_weights(h);
+  picnn_xpath_free(h);
   delete h;
   return ICNN_OK;
 }

@@ -138,6 +138,10 @@ struct TcArgs {
   const float* Cy; float* g; long long g_row_stride; const int* perm; const int* count; int KS; int n;
   float g_scale;
   float* C;  // mode 2
+  // mode 3 (x-path gate GEMM): out = acc + bias[col]; up to 4 column ranges [rbeg[r], rbeg[r+1]) each with
+  // its own ReLU flag and destination (row pitch rld[r]); range 0 may instead be written as a TF32
+  // hi/lo pair (the next u-layer operand)
+  int nr; int rbeg[5]; int rrelu[4]; float* rdst[4]; int rld[4]; float* r0_hi; float* r0_lo; const float* bias;
   const int* skip_if_zero;
 };
 
@@ -289,6 +293,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               const long long idx = (long long)m * a.N + nn;
               in0[i] = __ldg(a.D + idx);
               if (a.nxt_hi) in1[i] = __ldg(a.Cz_next + idx);
+            } else if (a.mode == 3) {
+              in0[i] = __ldg(a.bias + nn);
             } else if (a.mode == 1) {
               if (nn < a.N0) {
                 const long long idx = (long long)m * a.N0 + nn;
@@ -328,6 +334,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             } else {
               const int e = nn - a.N0;
               reinterpret_cast<float*>(gp[i])[e] = fmaf(a.g_scale * in0[i], acc[i], in1[i]);
+            }
+          } else if (a.mode == 3) {
+            int r = 0;
+#pragma unroll
+            for (int t = 1; t < 4; ++t) if (t < a.nr && nn >= a.rbeg[t]) r = t;
+            float v = acc[i] + in0[i];
+            if (a.rrelu[r]) v = fmaxf(v, 0.f);
+            const int c = nn - a.rbeg[r];
+            if (r == 0 && a.r0_hi) {
+              const float h = tf32_hi(v);
+              a.r0_hi[(long long)m * a.rld[0] + c] = h;
+              a.r0_lo[(long long)m * a.rld[0] + c] = v - h;
+            } else {
+              a.rdst[r][(long long)m * a.rld[r] + c] = v;
             }
           } else {
             a.C[(long long)m * a.N + nn] = acc[i];
@@ -450,9 +470,12 @@ static cudaError_t launch_tc_variant(const CUtensorMap& tAh, const CUtensorMap& 
 static int launch_tc_gemm(const float* Ah, const float* Al, long long lda, const float* Bh, const float* Bl, long long ldb,
                           TcArgs a, cudaStream_t st) {
   const int gy = cdiv(a.M, TC_BM);
-  // tile choice: 128-wide tiles when they still cover the chip, else 64-wide; 64-wide with two
-  // CTAs per SM once there are >= 2 tiles per SM.  ICNN_TC_CFG=128|64x4|64x2 forces one.
-  int cfg = (cdiv(a.N, 128) * gy >= 148 && a.N >= 128) ? 0 : ((cdiv(a.N, 64) * gy >= 296) ? 2 : 1);
+  // tile choice: 64-wide tiles; two CTAs per SM (the epilogue of one overlaps the main loop of the
+  // other) once there are >= 2 tiles per SM, else one CTA per SM with a 4-deep ring.
+  // ICNN_TC_CFG=128|64x4|64x2 forces a variant.
+  // (measured on B200, T shape: 64x2 4.28 ms, 128 5.12 ms, 64x4 6.62 ms per 10 iterations of K1;
+  //  C2, 28 tiles: 64x4 7.5 ms, 64x2 8.0 ms, 128 9.2 ms)
+  int cfg = (cdiv(a.N, 64) * gy >= 296) ? 2 : 1;
   if (const char* v = getenv("ICNN_TC_CFG")) {
     if (!strcmp(v, "128")) cfg = 0; else if (!strcmp(v, "64x4")) cfg = 1; else if (!strcmp(v, "64x2")) cfg = 2;
   }
@@ -571,9 +594,119 @@ int picnn_fg_tc(const icnn_picnn* h, const icnn_gates* gt, const float* y32, flo
   return ICNN_OK;
 }
 
+// ---- x-path (gate precompute) -------------------------------------------
+// One GEMM per source activation P_s (P_0 = x, P_s = u_{s-1}) against the N-concatenated weights
+//   [Wu_s | Wzu_s | Wyu_s | Wzx_s]   (multi-label-cls/icnn_ebundle.py:339-347,354-356,363-365,372-373)
+// kept transposed ([N_total, K], K-major) and TF32 hi/lo split; bias, ReLU and the scatter into
+// u / cz / cy / d are fused into the epilogue (mode 3).
+int picnn_xpath_prepare(icnn_picnn* h, int m, const float* const* Wu, const float* const* bu,
+                        const float* const* Wzu, const float* const* bzu, const float* const* Wyu,
+                        const float* const* byu, const float* const* Wzx, const float* const* bzx, cudaStream_t st) {
+  const int L = h->L, n = h->n;
+  h->m = m;
+  for (int s = 0; s <= L; ++s) {
+    const int K = s == 0 ? m : h->hidden[s - 1];
+    const int wu = s < L ? h->hidden[s] : 0, wzu = s >= 1 ? h->hidden[s - 1] : 0, wd = h->width(s);
+    const int Nt = wu + wzu + n + wd;
+    h->xN[s] = Nt; h->xK[s] = K;
+    for (float** p : {&h->Xw_hi[s], &h->Xw_lo[s]})
+      if (cudaMalloc(p, sizeof(float) * (size_t)Nt * K) != cudaSuccess) { set_error("cudaMalloc x-path weights"); return ICNN_E_CUDA; }
+    if (cudaMalloc(&h->Xbias[s], sizeof(float) * Nt) != cudaSuccess) { set_error("cudaMalloc x-path bias"); return ICNN_E_CUDA; }
+    int off = 0;
+    auto put = [&](const float* W, const float* bvec, int width) {   // W [K, width] row-major -> rows off.. of [Nt, K]
+      if (width == 0) return;
+      dim3 tb(32, 8), tg(cdiv(width, 32), cdiv(K, 32));
+      transpose_split_kernel<<<tg, tb, 0, st>>>(W, h->Xw_hi[s] + (size_t)off * K, h->Xw_lo[s] + (size_t)off * K, K, width);
+      cudaMemcpyAsync(h->Xbias[s] + off, bvec, sizeof(float) * width, cudaMemcpyDeviceToDevice, st);
+      off += width;
+    };
+    if (s < L) put(Wu[s], bu[s], wu);
+    if (s >= 1) put(Wzu[s], bzu[s], wzu);
+    put(Wyu[s], byu[s], n);
+    put(Wzx[s], bzx[s], wd);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("x-path prepare: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
+  h->has_xpath = true;
+  return ICNN_OK;
+}
+
+void picnn_xpath_free(icnn_picnn* h) {
+  for (int s = 0; s <= ICNN_MAX_LAYERS; ++s)
+    for (float** p : {&h->Xw_hi[s], &h->Xw_lo[s], &h->Xbias[s]})
+      if (*p) { cudaFree(*p); *p = nullptr; }
+}
+
+// workspace (floats): x hi/lo [B, m], u_s hi/lo [B, s_s] for s < L
+size_t picnn_xpath_ws_floats(const icnn_picnn* h, int B, size_t* off) {
+  size_t o = 0;
+  auto al = [](size_t v) { return (v + 63) & ~(size_t)63; };
+  for (int s = 0; s <= h->L; ++s) {
+    const size_t sz = al((size_t)B * (s == 0 ? h->m : h->hidden[s - 1]));
+    if (off) { off[2 * s] = o; off[2 * s + 1] = o + sz; }
+    o += 2 * sz;
+  }
+  return o;
+}
+
+int picnn_gates_tc(const icnn_picnn* h, const float* x, int B, float* const* cz, float* const* cy, float* const* d,
+                   void* workspace, cudaStream_t st) {
+  const int L = h->L, n = h->n;
+  size_t off[2 * (ICNN_MAX_LAYERS + 1)];
+  picnn_xpath_ws_floats(h, B, off);
+  float* ws = static_cast<float*>(workspace);
+  split_tf32_kernel<<<(unsigned)(((long long)B * h->m + 255) / 256), 256, 0, st>>>(x, ws + off[0], ws + off[1], (long long)B * h->m);
+  for (int s = 0; s <= L; ++s) {
+    const int wu = s < L ? h->hidden[s] : 0, wzu = s >= 1 ? h->hidden[s - 1] : 0, wd = h->width(s);
+    TcArgs a{};
+    a.M = B; a.N = h->xN[s]; a.K = h->xK[s]; a.mode = 3; a.bias = h->Xbias[s];
+    int r = 0, c = 0;
+    a.rbeg[0] = 0;
+    if (s < L) {   // u_s = (relu for s < L-1)(P Wu + bu): only needed as the next GEMM's hi/lo operand
+      a.rrelu[r] = (s < L - 1); a.rdst[r] = nullptr; a.rld[r] = wu; a.r0_hi = ws + off[2 * (s + 1)]; a.r0_lo = ws + off[2 * (s + 1) + 1];
+      c += wu; a.rbeg[++r] = c;
+    }
+    if (s >= 1) { a.rrelu[r] = 1; a.rdst[r] = cz[s]; a.rld[r] = wzu; c += wzu; a.rbeg[++r] = c; }
+    a.rrelu[r] = 0; a.rdst[r] = cy[s]; a.rld[r] = n; c += n; a.rbeg[++r] = c;
+    a.rrelu[r] = 0; a.rdst[r] = d[s]; a.rld[r] = wd; c += wd; a.rbeg[++r] = c;
+    a.nr = r;
+    int rc = launch_tc_gemm(ws + off[2 * s], ws + off[2 * s + 1], a.K, h->Xw_hi[s], h->Xw_lo[s], a.K, a, st);
+    if (rc) return rc;
+  }
+  return ICNN_OK;
+}
+
 }  // namespace icnn
 
 using namespace icnn;
+
+extern "C" int icnn_picnn_set_xpath(icnn_picnn_t* h, int32_t m, const float* const* Wu, const float* const* bu,
+                                    const float* const* Wzu, const float* const* bzu, const float* const* Wyu,
+                                    const float* const* byu, const float* const* Wzx, const float* const* bzx,
+                                    void* stream) {
+  ICNN_REQUIRE(h && Wu && bu && Wzu && bzu && Wyu && byu && Wzx && bzx, "null pointer");
+  ICNN_REQUIRE(m >= 1, "m must be positive");
+  if (!h->use_tc || (m % 4) != 0) { set_error("x-path kernel needs the tensor-core path and m %% 4 == 0"); return ICNN_E_UNSUPPORTED; }
+  if (h->has_xpath) picnn_xpath_free(h);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = picnn_xpath_prepare(h, m, Wu, bu, Wzu, bzu, Wyu, byu, Wzx, bzx, st);
+  if (rc) return rc;
+  ICNN_CUDA_CHECK(cudaStreamSynchronize(st));
+  return ICNN_OK;
+}
+
+extern "C" size_t icnn_picnn_gates_workspace_bytes(const icnn_picnn_t* h, int32_t B) {
+  if (!h || !h->has_xpath || B <= 0) return 0;
+  return sizeof(float) * picnn_xpath_ws_floats(h, B, nullptr);
+}
+
+extern "C" int icnn_picnn_gates(const icnn_picnn_t* h, const float* x, int32_t B, float* const* cz,
+                                float* const* cy, float* const* d, void* workspace, void* stream) {
+  ICNN_REQUIRE(h && x && cz && cy && d && workspace, "null pointer");
+  ICNN_REQUIRE(B > 0, "empty batch");
+  if (!h->has_xpath) { set_error("icnn_picnn_set_xpath was not called"); return ICNN_E_INVALID; }
+  return picnn_gates_tc(h, x, B, cz, cy, d, workspace, static_cast<cudaStream_t>(stream));
+}
 
 // Self test of the tensor-core GEMM: C[M,N] = A[M,K] * B[N,K]^T (3xTF32), all device, row-major.
 // scratch: 2*M*K + 2*N*K floats.

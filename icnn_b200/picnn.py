@@ -60,6 +60,18 @@ class PICNN:
             stream = torch.cuda.current_stream().cuda_stream
             _capi.check(_capi.lib.icnn_picnn_create(C.byref(desc), C.byref(handle), C.c_void_p(stream)))
         self._h = handle
+        # x-path gate precompute on the library's tcgen05 GEMM when the shapes allow it
+        # (SURVEY.md section 8f row 2); otherwise plain cuBLAS GEMMs through torch.addmm
+        self._xpath = False
+        with torch.cuda.device(self.device):
+            args = [_capi.ptr_array(v) for v in (self.Wu, self.bu, self.Wzu, self.bzu, self.Wyu, self.byu,
+                                                  self.Wzx, self.bzx)]
+            rc = _capi.lib.icnn_picnn_set_xpath(self._h, self.m, *[C.cast(a, _capi._fpp) for a in args],
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            if rc == 0:
+                self._xpath = True
+            elif rc != -3:           # -3 = ICNN_E_UNSUPPORTED (width not a multiple of 4 / SIMT-only build)
+                _capi.check(rc)
 
     @classmethod
     def from_params(cls, p, device=None):
@@ -86,6 +98,20 @@ class PICNN:
         (SURVEY.md section 8f row 2 lists a hand-written kernel for it as "next")."""
         x = _dev(x, self.device)
         L = self.L
+        if self._xpath:
+            B = int(x.shape[0])
+            e = lambda w: torch.empty(B, w, dtype=torch.float32, device=self.device)  # noqa: E731
+            cz = [None] + [e(self.hidden[i - 1]) for i in range(1, L + 1)]
+            cy = [e(self.n) for _ in range(L + 1)]
+            d = [e(self.hidden[i]) if i < L else e(1) for i in range(L + 1)]
+            nbytes = _capi.lib.icnn_picnn_gates_workspace_bytes(self._h, B)
+            ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=self.device)
+            pz, py, pd = _capi.ptr_array(cz), _capi.ptr_array(cy), _capi.ptr_array(d)
+            _capi.check(_capi.lib.icnn_picnn_gates(self._h, x.data_ptr(), B, C.cast(pz, _capi._fpp),
+                                                   C.cast(py, _capi._fpp), C.cast(pd, _capi._fpp), ws.data_ptr(),
+                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            self._gates_ws = ws     # keep alive until the stream has consumed it
+            return cz, cy, d
         us, prev = [], x
         for i in range(L):
             u = torch.addmm(self.bu[i], prev, self.Wu[i])

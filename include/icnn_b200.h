@@ -131,6 +131,21 @@ int icnn_picnn_fg(const icnn_picnn_t* h, const icnn_gates* gates, const float* y
                   float* g, int64_t g_row_stride, const int32_t* perm, const int32_t* count,
                   int32_t KS, void* workspace, const int32_t* skip_if_zero, void* stream);
 
+/* ---- x-path gate precompute ------------------------------------------ */
+/* replaces: the u-path and gate fully-connected layers of Model.f / Agent.negQ
+ * (multi-label-cls/icnn_ebundle.py:339-347,354-356,363-365,372-373), evaluated once per solveBatch.
+ * set_xpath hands the library the x-path weights (host arrays of device pointers, [in, out] layout;
+ * Wu/bu: L entries, the others L+1, Wzu[0]/bzu[0] ignored); gates() then fills cz/cy/d for a
+ * minibatch x [B, m] with one tcgen05 GEMM per source activation (bias, ReLU and the scatter into
+ * the outputs fused into the epilogue).  ICNN_E_UNSUPPORTED when a width is not a multiple of 4. */
+int icnn_picnn_set_xpath(icnn_picnn_t* h, int32_t m, const float* const* Wu, const float* const* bu,
+                         const float* const* Wzu, const float* const* bzu, const float* const* Wyu,
+                         const float* const* byu, const float* const* Wzx, const float* const* bzx,
+                         void* stream);
+size_t icnn_picnn_gates_workspace_bytes(const icnn_picnn_t* h, int32_t B);
+int icnn_picnn_gates(const icnn_picnn_t* h, const float* x, int32_t B, float* const* cz, float* const* cy,
+                     float* const* d, void* workspace, void* stream);
+
 /* ---- K2: bundle-entropy step ------------------------------------------------------------- */
 /* replaces: the per-sample loop body of solveBatch, lib/bundle_entropy.py:211-237 (and the dual /
  * RL copies), including pdipm_pc :5-78 / proj_newton_logistic. */

@@ -60,3 +60,29 @@ def test_gd_zero_iterations_returns_energy_of_y0():
     np.testing.assert_allclose(y, y0, atol=0)
     fo, _ = picnn_np.make_fg(p, x)(y0)
     np.testing.assert_allclose(f, fo, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name,B", [("C1", 64), ("T", 300), ("C2", 70), ("C5", 40)])
+def test_xpath_gates_kernel_matches_oracle(name, B):
+    """Gate precompute on the library's tcgen05 GEMM vs the float64 oracle
+    x-path (multi-label-cls/icnn_ebundle.py:339-373)."""
+    cfg, p, x, y0, net = _net(name, B)
+    assert net._xpath, "shape should take the tensor-core x-path"
+    cz, cy, d = net.gates(x)
+    ocz, ocy, od = picnn_np.gates(p, x)
+    for i in range(p.L + 1):
+        for got, want in ((cz[i], ocz[i]), (cy[i], ocy[i]), (d[i], od[i])):
+            if want is None:
+                assert got is None
+                continue
+            g = got.cpu().numpy().astype(np.float64)
+            assert g.shape == want.shape
+            assert np.abs(g - want).max() <= 1e-5 * max(1.0, np.abs(want).max())
+
+
+def test_xpath_falls_back_for_unaligned_widths():
+    cfg, p, x, y0, net = _net("C3", 16)      # n = 159: not TMA-compatible -> cuBLAS x-path, FFMA K1
+    assert not net._xpath
+    cz, cy, d = net.gates(x)
+    ocz, ocy, od = picnn_np.gates(p, x)
+    assert np.abs(cy[0].cpu().numpy() - ocy[0]).max() <= 1e-4 * max(1.0, np.abs(ocy[0]).max())
