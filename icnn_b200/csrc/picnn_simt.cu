@@ -229,9 +229,10 @@ __global__ void __launch_bounds__(256) out_layer_kernel(OutArgs a) {
     const float dl = (z > 0.f ? 1.f : a.alpha) * c;
     if (a.delta) a.delta[idx] = dl;
     if (a.delta_hi) {
-      const float h = __uint_as_float(__float_as_uint(dl) & 0xFFFFE000u);
+      // TF32 hi/lo with round-to-nearest on both parts (see tf32_rn in picnn_tc.cu)
+      const float h = __uint_as_float((__float_as_uint(dl) + 0x00001000u) & 0xFFFFE000u);
       a.delta_hi[idx] = h;
-      a.delta_lo[idx] = dl - h;
+      a.delta_lo[idx] = __uint_as_float((__float_as_uint(dl - h) + 0x00001000u) & 0xFFFFE000u);
     }
   }
   float* grow;

@@ -119,7 +119,12 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// TF32 split with round-to-nearest on both parts: hi = rn_tf32(x), lo = rn_tf32(x - hi), both exactly
+// representable in TF32 (the tensor core would otherwise TRUNCATE its inputs), so
+// |x - (hi + lo)| <= 2^-22 |x|  (measured: gates/f/g errors 2-4x lower than with truncation).
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x00001000u) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_hi(float x) { return tf32_rn(x); }
+__device__ __forceinline__ float tf32_lo(float x, float hi) { return tf32_rn(x - hi); }
 
 // ---------------------------------------------------------------------------------------------
 // the GEMM kernel
@@ -321,7 +326,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               const float p = z * in1[i];
               const float h = tf32_hi(p);
               a.nxt_hi[(long long)m * a.nxt_ld + nn] = h;
-              a.nxt_lo[(long long)m * a.nxt_ld + nn] = p - h;
+              a.nxt_lo[(long long)m * a.nxt_ld + nn] = tf32_lo(p, h);
             }
           } else if (a.mode == 1) {
             if (nn < a.N0) {
@@ -330,7 +335,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               const float p = da * in1[i] * acc[i];
               const float h = tf32_hi(p);
               a.dprev_hi[idx] = h;
-              a.dprev_lo[idx] = p - h;
+              a.dprev_lo[idx] = tf32_lo(p, h);
             } else {
               const int e = nn - a.N0;
               reinterpret_cast<float*>(gp[i])[e] = fmaf(a.g_scale * in0[i], acc[i], in1[i]);
@@ -345,7 +350,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             if (r == 0 && a.r0_hi) {
               const float h = tf32_hi(v);
               a.r0_hi[(long long)m * a.rld[0] + c] = h;
-              a.r0_lo[(long long)m * a.rld[0] + c] = v - h;
+              a.r0_lo[(long long)m * a.rld[0] + c] = tf32_lo(v, h);
             } else {
               a.rdst[r][(long long)m * a.rld[r] + c] = v;
             }
@@ -386,7 +391,7 @@ __global__ void gate_y_kernel(GateYArgs a) {
     const float p = yy * a.cy[l][i];
     const float h = tf32_hi(p);
     a.hi[l][(long long)m * a.ld[l] + a.off[l] + e] = h;
-    a.lo[l][(long long)m * a.ld[l] + a.off[l] + e] = p - h;
+    a.lo[l][(long long)m * a.ld[l] + a.off[l] + e] = tf32_lo(p, h);
   }
 }
 
@@ -395,7 +400,7 @@ __global__ void split_tf32_kernel(const float* src, float* hi, float* lo, long l
   if (i >= N) return;
   const float x = src[i], h = tf32_hi(x);
   hi[i] = h;
-  lo[i] = x - h;
+  lo[i] = tf32_lo(x, h);
 }
 // dst[c, r] = src[r, c] split hi/lo   (src [R, C] row-major -> dst [C, R])
 __global__ void transpose_split_kernel(const float* src, float* hi, float* lo, int R, int C) {
@@ -411,7 +416,7 @@ __global__ void transpose_split_kernel(const float* src, float* hi, float* lo, i
     if (c < C && r < R) {
       const float x = tile[threadIdx.x][i], h = tf32_hi(x);
       hi[(long long)c * R + r] = h;
-      lo[(long long)c * R + r] = x - h;
+      lo[(long long)c * R + r] = tf32_lo(x, h);
     }
   }
 }

@@ -142,7 +142,9 @@ def test_k2_against_reference_golden(case, maxtol, medtol, golden_dir):
         assert agree >= (0.5 if nIter > 10 else 0.8), agree
 
 
-FUSED = [("C1", 64, 5, 1e-4), ("C4", 512, 5, 1e-4), ("T", 48, 10, 1e-4), ("C3", 96, 10, None), ("C2", 6, 30, None)]
+# ("T", 160, ...) and ("C2", 70, ...) have >= 64 rows: K1 and the gate precompute run on the tcgen05 path
+FUSED = [("C1", 64, 5, 1e-4), ("C4", 512, 5, 1e-4), ("T", 48, 10, 1e-4), ("T", 160, 10, None), ("C3", 96, 10, None),
+         ("C2", 6, 30, None), ("C2", 70, 8, None)]
 
 
 @pytest.mark.parametrize("name,B,nIter,maxtol", FUSED)
