@@ -74,6 +74,20 @@ struct Grp {
     cl.sync();
     return r;
   }
+  // two minima in one exchange (the step bounds of y and 1-y)
+  __device__ __forceinline__ void cmin2(double& a, double& b) const {
+    a = wmin(a); b = wmin(b);
+    if (WPS > 1) {
+      if (lane == 0) { red[warp] = a; red[WPS + warp] = b; }
+      sync();
+      double ra = red[0], rb = red[WPS];
+#pragma unroll
+      for (int w = 1; w < WPS; ++w) { ra = fmin(ra, red[w]); rb = fmin(rb, red[WPS + w]); }
+      sync();
+      a = ra; b = rb;
+    }
+    if (CS > 1) { a = cfold(a, 1); b = cfold(b, 1); }
+  }
   __device__ __forceinline__ double csum(double v) const { return cfold(sum(v), 0); }
   __device__ __forceinline__ double cmin(double v) const { return cfold(min(v), 1); }
   __device__ __forceinline__ double cmax(double v) const { return cfold(max(v), 2); }
@@ -301,10 +315,10 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // gram pass (fallback, any n): warp owns 4x4 blocks of M = G diag(w) G^T, lanes stride columns.
 template <int WPS, class G>
 __device__ inline void gram_pass_simt(const G& g, const float* const* rowp, int k, int n,
-                                      const double* w, double* M, int ld) {
+                                      const double* w, double* M, int ld, int widx, int nw) {
   const int kb = (k + 3) >> 2;
   const int nblk = kb * (kb + 1) / 2;
-  for (int blk = g.warp; blk < nblk; blk += WPS) {
+  for (int blk = (widx < 0 ? nblk : widx); blk < nblk; blk += nw) {
     int bi = 0, rem = blk;
     while (rem >= kb - bi) { rem -= kb - bi; ++bi; }
     const int bj = bi + rem;
@@ -350,7 +364,7 @@ __device__ inline void gram_pass_simt(const G& g, const float* const* rowp, int 
 // M in warp order (deterministic).
 template <int WPS, int NA, int NB, bool TRI, class G>
 __device__ inline void gram_sweep(const G& g, const float* const* rowp, int k, int n,
-                                  const double* w, double* M, int ld, int a0, int b0) {
+                                  const double* w, double* M, int ld, int a0, int b0, int widx, int nw) {
   constexpr int NT = TRI ? NA * (NA + 1) / 2 : NA * NB;
   constexpr int NL = TRI ? NB : NA + NB;   // row blocks to load (TRI: A and B blocks coincide)
   double acc[NT][2];
@@ -367,7 +381,7 @@ __device__ inline void gram_sweep(const G& g, const float* const* rowp, int k, i
     rp[b] = rowp[rok[b] ? row : k - 1] + 4 * q;
   }
   const int ngrp = (n + 15) >> 4;
-  for (int gi = g.warp; gi < ngrp; gi += WPS) {
+  for (int gi = (widx < 0 ? ngrp : widx); gi < ngrp; gi += nw) {
     const int col = gi * 16 + 4 * q;
     const bool cv = col < n;  // n % 4 == 0: the whole float4 is in or out
     float4 v[NL];
@@ -398,8 +412,8 @@ __device__ inline void gram_sweep(const G& g, const float* const* rowp, int k, i
     }
   }
   // ordered accumulation of the warp partials into M (symmetric fill)
-  for (int wi = 0; wi < WPS; ++wi) {
-    if (g.warp == wi) {
+  for (int wi = 0; wi < nw; ++wi) {
+    if (widx == wi) {
       int t = 0;
 #pragma unroll
       for (int i = 0; i < NA; ++i)
@@ -423,27 +437,29 @@ __device__ inline void gram_sweep(const G& g, const float* const* rowp, int k, i
 
 template <int WPS, int NB, class G>
 __device__ inline void gram_rect_pair(const G& g, const float* const* rowp, int k, int n,
-                                      const double* w, double* M, int ld) {
-  gram_sweep<WPS, 2, NB, false>(g, rowp, k, n, w, M, ld, 0, 4);
-  gram_sweep<WPS, 2, NB, false>(g, rowp, k, n, w, M, ld, 2, 4);
+                                      const double* w, double* M, int ld, int widx, int nw) {
+  gram_sweep<WPS, 2, NB, false>(g, rowp, k, n, w, M, ld, 0, 4, widx, nw);
+  gram_sweep<WPS, 2, NB, false>(g, rowp, k, n, w, M, ld, 2, 4, widx, nw);
 }
 
+// Warps widx = 0..nw-1 of the group sweep the Gram (the others -- widx < 0 -- only take part in the
+// barriers), so that a row pass can run on the remaining warps at the same time.
 template <int WPS, class G>
 __device__ inline void gram_pass(const G& g, const float* const* rowp, int k, int n,
-                                 const double* w, double* M, int ld) {
-  if ((n & 3) != 0) { gram_pass_simt<WPS>(g, rowp, k, n, w, M, ld); g.sync(); return; }
+                                 const double* w, double* M, int ld, int widx, int nw) {
+  if ((n & 3) != 0) { gram_pass_simt<WPS>(g, rowp, k, n, w, M, ld, widx, nw); g.sync(); return; }
   const int rb = (k + 7) >> 3;   // <= 8 (KS <= 64)
-  if (rb == 1) gram_sweep<WPS, 1, 1, true>(g, rowp, k, n, w, M, ld, 0, 0);
-  else if (rb == 2) gram_sweep<WPS, 2, 2, true>(g, rowp, k, n, w, M, ld, 0, 0);
-  else if (rb == 3) gram_sweep<WPS, 3, 3, true>(g, rowp, k, n, w, M, ld, 0, 0);
+  if (rb == 1) gram_sweep<WPS, 1, 1, true>(g, rowp, k, n, w, M, ld, 0, 0, widx, nw);
+  else if (rb == 2) gram_sweep<WPS, 2, 2, true>(g, rowp, k, n, w, M, ld, 0, 0, widx, nw);
+  else if (rb == 3) gram_sweep<WPS, 3, 3, true>(g, rowp, k, n, w, M, ld, 0, 0, widx, nw);
   else {
-    gram_sweep<WPS, 4, 4, true>(g, rowp, k, n, w, M, ld, 0, 0);
+    gram_sweep<WPS, 4, 4, true>(g, rowp, k, n, w, M, ld, 0, 0, widx, nw);
     if (rb > 4) {   // rows 32..k-1: second triangle + the 4 x (rb-4) rectangle in two halves
       const int r2 = rb - 4;
-      if (r2 == 1) { gram_sweep<WPS, 1, 1, true>(g, rowp, k, n, w, M, ld, 4, 4); gram_rect_pair<WPS, 1>(g, rowp, k, n, w, M, ld); }
-      else if (r2 == 2) { gram_sweep<WPS, 2, 2, true>(g, rowp, k, n, w, M, ld, 4, 4); gram_rect_pair<WPS, 2>(g, rowp, k, n, w, M, ld); }
-      else if (r2 == 3) { gram_sweep<WPS, 3, 3, true>(g, rowp, k, n, w, M, ld, 4, 4); gram_rect_pair<WPS, 3>(g, rowp, k, n, w, M, ld); }
-      else { gram_sweep<WPS, 4, 4, true>(g, rowp, k, n, w, M, ld, 4, 4); gram_rect_pair<WPS, 4>(g, rowp, k, n, w, M, ld); }
+      if (r2 == 1) { gram_sweep<WPS, 1, 1, true>(g, rowp, k, n, w, M, ld, 4, 4, widx, nw); gram_rect_pair<WPS, 1>(g, rowp, k, n, w, M, ld, widx, nw); }
+      else if (r2 == 2) { gram_sweep<WPS, 2, 2, true>(g, rowp, k, n, w, M, ld, 4, 4, widx, nw); gram_rect_pair<WPS, 2>(g, rowp, k, n, w, M, ld, widx, nw); }
+      else if (r2 == 3) { gram_sweep<WPS, 3, 3, true>(g, rowp, k, n, w, M, ld, 4, 4, widx, nw); gram_rect_pair<WPS, 3>(g, rowp, k, n, w, M, ld, widx, nw); }
+      else { gram_sweep<WPS, 4, 4, true>(g, rowp, k, n, w, M, ld, 4, 4, widx, nw); gram_rect_pair<WPS, 4>(g, rowp, k, n, w, M, ld, widx, nw); }
     }
   }
 }
@@ -468,6 +484,8 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
   g.lane = threadIdx.x & 31;
   g.warp = g.tid >> 5;
   g.gid = threadIdx.x / T;
+  constexpr int NWG = (WPS >= 2) ? WPS / 2 : 1;                  // warps that sweep the Gram
+  const int WIDX = (WPS == 1) ? 0 : (g.warp < NWG ? g.warp : -1);
   const int crank = (CS == 1) ? 0 : (int)cg::this_cluster().block_rank();
   const int u = (CS == 1) ? blockIdx.x * GPB + g.gid : (int)(blockIdx.x / CS);
   if (u >= b.B) return;
@@ -691,8 +709,9 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
       });
       pr = g.sum(pr);   // local; (contains the barrier that publishes rv / dv)
       if (WPS == 1) __syncwarp();
-      // row pass: rd = G y + h - t + s ; q = G D ry
-      for (int j = g.warp; j < k; j += WPS) {
+      // row pass (rd = G y + h - t + s ; q = G D ry) on the upper half of the group's warps while
+      // the lower half sweeps the weighted Gram on the FP64 tensor cores (both only read G, y, D, ry)
+      for (int j = (WPS == 1 ? 0 : g.warp - NWG); j < k && j >= 0; j += (WPS == 1 ? 1 : WPS - NWG)) {
         const float* rj = rowp[j];
         double a1 = 0.0, a2 = 0.0;
         for (int e = g.lane; e < n; e += 32) {
@@ -704,8 +723,7 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
         a2 = Grp<WPS>::wsum(a2);
         if (g.lane == 0) { rdk[j] = a1; qk[j] = a2; }   // column sums only; h - t + s is added below
       }
-      // weighted Gram (independent of the row pass: reads only G and dv)
-      gram_pass<WPS>(g, rowp, k, n, dv, M, ld);
+      gram_pass<WPS>(g, rowp, k, n, dv, M, ld, WIDX, NWG);
       g.sync();
       if (CS > 1) {   // one exchange: M, (G y, G D ry) and the squared residual norm
         if (g.tid == 0) sc[11] = pr;
@@ -769,8 +787,7 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
         if (dy < 0.0) st = fmin(st, ratio);
         if (dy > 0.0) st2 = fmin(st2, ratio);
       });
-      st = g.cmin(st);
-      st2 = g.cmin(st2);
+      g.cmin2(st, st2);
       st = fmin(st > 1e299 ? 1.0 : st, st2 > 1e299 ? 1.0 : st2);
       if (g.warp == 0) {
         const int lane = g.lane;
@@ -821,8 +838,7 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
         if (dy < 0.0) st = fmin(st, ratio);
         if (dy > 0.0) st2 = fmin(st2, ratio);
       });
-      st = g.cmin(st);
-      st2 = g.cmin(st2);
+      g.cmin2(st, st2);
       st = fmin(st > 1e299 ? 1.0 : st, st2 > 1e299 ? 1.0 : st2);
       if (g.warp == 0) {
         const int lane = g.lane;
@@ -863,15 +879,15 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
         });
         fs = g.csum(fs);
         if (WPS == 1) __syncwarp();
-        // row pass: grad = -c + G z
-        for (int j = g.warp; j < k; j += WPS) {
+        // row pass: grad = -c + G z  (upper half of the warps; the lower half sweeps the Gram)
+        for (int j = (WPS == 1 ? 0 : g.warp - NWG); j < k && j >= 0; j += (WPS == 1 ? 1 : WPS - NWG)) {
           const float* rj = rowp[j];
           double acc = 0.0;
           for (int e = g.lane; e < n; e += 32) acc = fma((double)ldf(rj + e), yv[e], acc);
           acc = Grp<WPS>::wsum(acc);
           if (g.lane == 0) gk[j] = acc;   // G z (column sums only); -c is added below
         }
-        gram_pass<WPS>(g, rowp, k, n, dv, M, ld);
+        gram_pass<WPS>(g, rowp, k, n, dv, M, ld, WIDX, NWG);
         g.sync();
         g.cvsum(M, k * ld, gk, k);
         for (int j = g.tid; j < k; j += T) gk[j] -= ck[j];   // grad = -c + G z
@@ -1147,7 +1163,7 @@ __global__ void __launch_bounds__(256, 2) argmin_grad_kernel(GradArgs A) {
     acc = Grp<WPS>::wsum(acc);
     if (g.lane == 0) bk[j] = acc;
   }
-  gram_pass<WPS>(g, rowp, k, n, dv, M, ld);
+  gram_pass<WPS>(g, rowp, k, n, dv, M, ld, g.warp, WPS);
   g.sync();
   if (g.warp == 0) {
     const int lane = g.lane, m = k + 1;
