@@ -1323,7 +1323,14 @@ static cudaError_t launch_k2(const StepArgs& a, const K2Config& c, int B, cudaSt
   return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
+bool bundle_step_small_ok(const icnn_bundle_bufs* b);
+int bundle_step_small_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int t, cudaStream_t st);
+
 int bundle_step_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int t, cudaStream_t st) {
+  {  // tiny problems: one thread per sample (bundle_step_small.cu); ICNN_K2_SMALL=0 forces the group kernel
+    const char* v = getenv("ICNN_K2_SMALL");
+    if (!(v && v[0] == '0') && bundle_step_small_ok(b)) return bundle_step_small_launch(cfg, b, t, st);
+  }
   if (b->KS > 64) { set_error("bundle_step: KS=%d > 64 unsupported", b->KS); return ICNN_E_UNSUPPORTED; }
   K2Config c;
   int rc = pick_k2(b, &c);

@@ -291,3 +291,19 @@ def test_resident_cluster_variant_matches_streaming(name, B, nIter, env, monkeyp
     same = (lens(ref[1]) == lens(alt[1])) & (np.array(ref[5]) == np.array(alt[5]))
     assert same.mean() >= 0.8
     assert rowdiff(ref[0], alt[0])[same].max() < 1e-9
+
+
+@pytest.mark.parametrize("name,B,nIter,variant", [("C1", 64, 5, "lib"), ("C1", 64, 8, "dual"), ("C4", 300, 5, "rl")])
+def test_thread_per_sample_kernel_matches_group_kernel(name, B, nIter, variant, monkeypatch):
+    """n_y <= 8 runs the one-thread-per-sample K2 (bundle_step_small.cu); ICNN_K2_SMALL=0 forces the
+    warp-per-sample kernel.  Same algorithm, different summation order."""
+    from icnn_b200 import bundle_entropy as be
+    cfg = synth.CONFIGS[name]
+    p, x, y0 = synth.make_inputs(name, B=B)
+    fg = r32(picnn_np.make_fg(p, x, affine=cfg["affine"]))
+    small = be.solveBatch(fg, y0.copy(), nIter=nIter, variant=variant)
+    monkeypatch.setenv("ICNN_K2_SMALL", "0")
+    group = be.solveBatch(fg, y0.copy(), nIter=nIter, variant=variant)
+    same = (lens(small[1]) == lens(group[1])) & (np.array(small[5]) == np.array(group[5]))
+    assert same.mean() >= 0.9
+    assert rowdiff(small[0], group[0])[same].max() < 1e-9
