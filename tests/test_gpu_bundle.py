@@ -306,4 +306,5 @@ def test_thread_per_sample_kernel_matches_group_kernel(name, B, nIter, variant, 
     group = be.solveBatch(fg, y0.copy(), nIter=nIter, variant=variant)
     same = (lens(small[1]) == lens(group[1])) & (np.array(small[5]) == np.array(group[5]))
     assert same.mean() >= 0.9
-    assert rowdiff(small[0], group[0])[same].max() < 1e-9
+    # the RL Newton stops on |tau d| < 1e-10 / 20 iterations, so summation-order noise shows at 1e-7
+    assert rowdiff(small[0], group[0])[same].max() < (1e-6 if variant == "rl" else 1e-9)
