@@ -287,8 +287,8 @@ def run_gpu(args):
     # ---- end to end through the public API, host buffers -------------------------------------
     def step_e2e():
         fg_h = net.bind(x_pin, affine=cfg["affine"])            # H2D x + x-path gate precompute
-        out = bundle_entropy.solveBatch(fg_h, y0_pin.numpy().copy(), nIter=nIter, solver=solver,
-                                        variant=variant, return_state=True)   # H2D y0 ... D2H y*
+        out = bundle_entropy.solveBatch(fg_h, y0_pin, nIter=nIter, solver=solver,
+                                        variant=variant, return_state=True)   # H2D y0 (pinned) ... D2H y*
         if world > 1:
             dist.all_gather_into_tensor(y_all, out[-1].y)
         return out

@@ -10,6 +10,6 @@ package without the built library raises ImportError -- there is no CPU fallback
 """
 from . import _capi  # noqa: F401  (fails loudly if the native library is missing)
 from .picnn import PICNN, BoundPICNN  # noqa: F401
-from . import bundle_entropy, gd, argmin_grad  # noqa: F401
+from . import bundle_entropy, gd, argmin_grad, adam  # noqa: F401
 
-__all__ = ["PICNN", "BoundPICNN", "bundle_entropy", "gd", "argmin_grad"]
+__all__ = ["PICNN", "BoundPICNN", "bundle_entropy", "gd", "argmin_grad", "adam"]

@@ -27,6 +27,7 @@ SYMBOLS = [
     "icnn_bundle_init", "icnn_bundle_put_fg", "icnn_bundle_step",
     "icnn_solve_batch_fused", "icnn_gd_solve", "icnn_tc_gemm_selftest", "icnn_argmin_grad",
     "icnn_picnn_set_xpath", "icnn_picnn_gates_workspace_bytes", "icnn_picnn_gates",
+    "icnn_adam_workspace_bytes", "icnn_adam_solve",
 ]
 
 _fpp = C.POINTER(C.c_void_p)
@@ -90,6 +91,10 @@ def _load():
     lib.icnn_picnn_gates_workspace_bytes.argtypes = [C.c_void_p, C.c_int32]
     lib.icnn_picnn_gates_workspace_bytes.restype = C.c_size_t
     lib.icnn_picnn_gates.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, _fpp, _fpp, _fpp, C.c_void_p, C.c_void_p]
+    lib.icnn_adam_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.icnn_adam_workspace_bytes.restype = C.c_size_t
+    lib.icnn_adam_solve.argtypes = [C.c_void_p, C.POINTER(Gates), C.c_void_p, C.c_void_p, C.c_int32,
+                                    C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.icnn_argmin_grad.argtypes = [C.POINTER(BundleBufs), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
     for name in SYMBOLS:

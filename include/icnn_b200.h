@@ -177,6 +177,17 @@ int icnn_gd_solve(const icnn_picnn_t* h, const icnn_gates* gates, float* y32, fl
                   float* f_out, int32_t nIter, float lr, float momentum, void* workspace,
                   void* stream);
 
+/* ---- RL Adam argmin -------------------------------------------------- */
+/* replaces: Agent.adam (RL/src/icnn.py:160-215) applied to [negQ - entropy(act), d/dact]
+ * (RL/src/icnn.py:60-63,127-131,455-458): batched Adam on the actions with best-so-far tracking and
+ * the rolling-average stop, looped on the device (the stop flag is read back every 16 iterations).
+ * gates must be bound WITHOUT the affine wrapper (the network sees act in [-1,1] directly).
+ * act_best [B, n] f64 and f_best [B] f64 are outputs; iters_out (host) gets the reference's iteration
+ * count; scratch = icnn_adam_workspace_bytes(B, n) device bytes, workspace = icnn_picnn_workspace_bytes. */
+size_t icnn_adam_workspace_bytes(int32_t B, int32_t n);
+int icnn_adam_solve(const icnn_picnn_t* h, const icnn_gates* gates, double* act_best, double* f_best,
+                    int32_t max_iter, int32_t* iters_out, void* scratch, void* workspace, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 /* Self test of the tcgen05 / TMA GEMM the tensor-core K1 path is built from:
  * C[M,N] = A[M,K] * B[N,K]^T with the 3xTF32 split (all row-major device buffers, K % 4 == 0;
