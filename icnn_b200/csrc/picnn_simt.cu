@@ -214,39 +214,55 @@ struct OutArgs {
   const int* skip_if_zero;
 };
 
-// warp per sample: f = d_L + (z o cz_L).wz_L + (y o cy_L).wy_L ; seeds delta_{L-1} and g.
+// TPS threads per sample (32 = a warp, 256 = a CTA for small batches where a warp per sample is
+// latency-bound): f = d_L + (z o cz_L).wz_L + (y o cy_L).wy_L ; seeds delta_{L-1} and g.
+template <int TPS>
 __global__ void __launch_bounds__(256) out_layer_kernel(OutArgs a) {
   if (a.skip_if_zero != nullptr && *a.skip_if_zero == 0) return;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  __shared__ float red[8];
+  const int m = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) / TPS);
+  const int tl = threadIdx.x % TPS;
   const int lane = threadIdx.x & 31;
-  if (warp >= a.M) return;
-  const int m = warp;
+  const bool mv = m < a.M;
   float acc = 0.f;
-  for (int j = lane; j < a.S; j += 32) {
-    const long long idx = (long long)m * a.S + j;
-    const float z = a.Z[idx], c = a.Cz[idx] * a.w[j];
-    acc = fmaf(z, c, acc);
-    const float dl = (z > 0.f ? 1.f : a.alpha) * c;
-    if (a.delta) a.delta[idx] = dl;
-    if (a.delta_hi) {
-      // TF32 hi/lo with round-to-nearest on both parts (see tf32_rn in picnn_tc.cu)
-      const float h = __uint_as_float((__float_as_uint(dl) + 0x00001000u) & 0xFFFFE000u);
-      a.delta_hi[idx] = h;
-      a.delta_lo[idx] = __uint_as_float((__float_as_uint(dl - h) + 0x00001000u) & 0xFFFFE000u);
+  if (mv) {
+    for (int j = tl; j < a.S; j += TPS) {
+      const long long idx = (long long)m * a.S + j;
+      const float z = a.Z[idx], c = a.Cz[idx] * a.w[j];
+      acc = fmaf(z, c, acc);
+      const float dl = (z > 0.f ? 1.f : a.alpha) * c;
+      if (a.delta) a.delta[idx] = dl;
+      if (a.delta_hi) {
+        // TF32 hi/lo with round-to-nearest on both parts (see tf32_rn in picnn_tc.cu)
+        const float h = __uint_as_float((__float_as_uint(dl) + 0x00001000u) & 0xFFFFE000u);
+        a.delta_hi[idx] = h;
+        a.delta_lo[idx] = __uint_as_float((__float_as_uint(dl - h) + 0x00001000u) & 0xFFFFE000u);
+      }
     }
-  }
-  float* grow;
-  if (a.perm == nullptr) grow = a.g + (long long)m * a.g_row_stride;
-  else grow = a.g + ((long long)m * a.KS + a.perm[(long long)m * a.KS + a.count[m]]) * a.n;
-  for (int e = lane; e < a.n; e += 32) {
-    const long long idx = (long long)m * a.n + e;
-    const float c = a.Cy[idx] * a.w[a.S + e];
-    acc = fmaf(fmaf(a.in_scale, a.y[idx], a.in_shift), c, acc);
-    grow[e] = a.g_scale * c;
+    float* grow;
+    if (a.perm == nullptr) grow = a.g + (long long)m * a.g_row_stride;
+    else grow = a.g + ((long long)m * a.KS + a.perm[(long long)m * a.KS + a.count[m]]) * a.n;
+    for (int e = tl; e < a.n; e += TPS) {
+      const long long idx = (long long)m * a.n + e;
+      const float c = a.Cy[idx] * a.w[a.S + e];
+      acc = fmaf(fmaf(a.in_scale, a.y[idx], a.in_shift), c, acc);
+      grow[e] = a.g_scale * c;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) a.f[m] = acc + a.D[m];
+  if (TPS == 32) {
+    if (mv && lane == 0) a.f[m] = acc + a.D[m];
+  } else {   // TPS == 256: one sample per CTA, fixed-order sum of the 8 warp partials
+    if (lane == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0 && mv) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w];
+      a.f[m] = s + a.D[m];
+    }
+  }
 }
 
 __global__ void concat_rows_kernel(float* dst, const float* top, long long ntop, const float* bot,
@@ -310,7 +326,8 @@ void out_layer_launch(const icnn_picnn* h, const icnn_gates* gt, const float* Zl
   o.D = gt->d[L]; o.w = h->Wcat[L]; o.in_scale = gt->in_scale; o.in_shift = gt->in_shift;
   o.g_scale = gt->g_scale; o.alpha = h->alpha; o.f = f; o.delta = delta; o.delta_hi = delta_hi; o.delta_lo = delta_lo;
   o.g = g; o.g_row_stride = g_row_stride; o.perm = perm; o.count = count; o.KS = KS; o.skip_if_zero = skip;
-  out_layer_kernel<<<cdiv(B * 32, 256), 256, 0, st>>>(o);
+  if (B <= 2048) out_layer_kernel<256><<<B, 256, 0, st>>>(o);          // few samples: a CTA each
+  else out_layer_kernel<32><<<cdiv(B * 32, 256), 256, 0, st>>>(o);
 }
 
 bool picnn_tc_supported(const icnn_picnn* h);

@@ -21,9 +21,12 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <cooperative_groups.h>
 
 #include <cstdlib>
 #include <cstring>
+
+namespace cg = cooperative_groups;
 
 namespace icnn {
 
@@ -168,21 +171,26 @@ __global__ void __launch_bounds__(192, (BN == 64 && NST_ == 2) ? 2 : 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, TcArgs a) {
   if (a.skip_if_zero != nullptr && *a.skip_if_zero == 0) return;
-  using S = TcSmem<BN, NST_>;
+  using SM = TcSmem<BN, NST_>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
-  uint64_t* empty = full + S::NST;
-  uint64_t* tmem_full = empty + S::NST;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint64_t* empty = full + SM::NST;
+  uint64_t* tmem_full = empty + SM::NST;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-  const int nkb = (a.K + TC_BK - 1) / TC_BK;
+  // split-K: gridDim.z = S CTAs of one cluster share the output tile, each reduces a K-slice into its
+  // own TMEM accumulators; the partial tiles are summed through distributed shared memory below
+  const int S = gridDim.z;
+  const int nkb_all = (a.K + TC_BK - 1) / TC_BK;
+  const int kb0 = (int)(((long long)nkb_all * blockIdx.z) / S);
+  const int nkb = (int)(((long long)nkb_all * (blockIdx.z + 1)) / S) - kb0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
-    for (int s = 0; s < S::NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < SM::NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -199,15 +207,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S::NST;
-        const uint32_t ph = (kb / S::NST) & 1;
+        const int s = kb % SM::NST;
+        const uint32_t ph = (kb / SM::NST) & 1;
         mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], S::STAGE_BYTES);
-        uint8_t* st = smem + s * S::STAGE_BYTES;
-        tma_load_2d(st, &tmAh, &full[s], kb * TC_BK, m0);
-        tma_load_2d(st + S::A_BYTES, &tmAl, &full[s], kb * TC_BK, m0);
-        tma_load_2d(st + 2 * S::A_BYTES, &tmBh, &full[s], kb * TC_BK, n0);
-        tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, &full[s], kb * TC_BK, n0);
+        mbar_expect_tx(&full[s], SM::STAGE_BYTES);
+        uint8_t* st = smem + s * SM::STAGE_BYTES;
+        const int kc = (kb0 + kb) * TC_BK;
+        tma_load_2d(st, &tmAh, &full[s], kc, m0);
+        tma_load_2d(st + SM::A_BYTES, &tmAl, &full[s], kc, m0);
+        tma_load_2d(st + 2 * SM::A_BYTES, &tmBh, &full[s], kc, n0);
+        tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmBl, &full[s], kc, n0);
       }
     }
     __syncwarp();
@@ -215,15 +224,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S::NST;
-        const uint32_t ph = (kb / S::NST) & 1;
+        const int s = kb % SM::NST;
+        const uint32_t ph = (kb / SM::NST) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t st = smem_u32(smem + s * SM::STAGE_BYTES);
         const uint64_t dAh = make_kmajor_sw128_desc(st);
-        const uint64_t dAl = make_kmajor_sw128_desc(st + S::A_BYTES);
-        const uint64_t dBh = make_kmajor_sw128_desc(st + 2 * S::A_BYTES);
-        const uint64_t dBl = make_kmajor_sw128_desc(st + 2 * S::A_BYTES + S::B_BYTES);
+        const uint64_t dAl = make_kmajor_sw128_desc(st + SM::A_BYTES);
+        const uint64_t dBh = make_kmajor_sw128_desc(st + 2 * SM::A_BYTES);
+        const uint64_t dBl = make_kmajor_sw128_desc(st + 2 * SM::A_BYTES + SM::B_BYTES);
 #pragma unroll
         for (int k4 = 0; k4 < TC_BK / 8; ++k4) {
           const uint64_t adv = (uint64_t)((k4 * 8 * 4) >> 4);  // +32 B per k-step inside the swizzle span
@@ -259,6 +268,67 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         growp = reinterpret_cast<unsigned long long>(gp);
       }
     }
+    if (S > 1) {
+      // ---- split-K epilogue: partial tile -> shared memory -> DSMEM sum -> fused epilogue ----
+      // (every CTA of the cluster reaches both cluster barriers: warps 0/1 call them below)
+      float* P = reinterpret_cast<float*>(smem);                  // [128][BN + 1] floats in the idle ring
+      constexpr int PP = BN + 1;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32], w[32];
+        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        if (nkb > 0) tmem_ld32(tb, v);
+        else { for (int j = 0; j < 32; ++j) v[j] = 0u; }
+        if (nsteps > 1) { tmem_ld32(tb + BN, w); for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j])); }
+        if (nsteps > 2) { tmem_ld32(tb + 2 * BN, w); for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j])); }
+        if (nkb > 0) { tmem_ld32(tb + 3 * BN, w); for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j])); }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) P[(q * 32 + lane) * PP + c0 + j] = __uint_as_float(v[j]);
+      }
+      tc_fence_before();
+      cg::this_cluster().sync();
+      cg::cluster_group cl = cg::this_cluster();
+      const int rank = (int)cl.block_rank();
+      const int rlo = (TC_BM * rank) / S, rhi = (TC_BM * (rank + 1)) / S;
+      for (int rr = rlo + q; rr < rhi; rr += 4) {                // this warp's rows of the CTA's row slice
+        const int m = m0 + rr;
+        if (m >= a.M) break;
+        float* grow = nullptr;
+        if (a.mode == 1)
+          grow = (a.perm == nullptr) ? a.g + (long long)m * a.g_row_stride
+                                     : a.g + ((long long)m * a.KS + a.perm[(long long)m * a.KS + a.count[m]]) * a.n;
+        for (int c = lane; c < BN; c += 32) {
+          const int nn = n0 + c;
+          if (nn >= a.N) break;
+          float acc = 0.f;
+          for (int qq = 0; qq < S; ++qq) acc += *cl.map_shared_rank(P + rr * PP + c, qq);
+          if (a.mode == 0) {
+            const long long idx = (long long)m * a.N + nn;
+            const float x = acc + __ldg(a.D + idx);
+            const float z = x > 0.f ? x : a.alpha * x;
+            a.Z[idx] = z;
+            if (a.nxt_hi) {
+              const float p = z * __ldg(a.Cz_next + idx);
+              const float h = tf32_hi(p);
+              a.nxt_hi[(long long)m * a.nxt_ld + nn] = h;
+              a.nxt_lo[(long long)m * a.nxt_ld + nn] = tf32_lo(p, h);
+            }
+          } else {
+            if (nn < a.N0) {
+              const long long idx = (long long)m * a.N0 + nn;
+              const float da = __ldg(a.Zprev + idx) > 0.f ? 1.f : a.alpha;
+              const float p = da * __ldg(a.Cz + idx) * acc;
+              const float h = tf32_hi(p);
+              a.dprev_hi[idx] = h;
+              a.dprev_lo[idx] = tf32_lo(p, h);
+            } else {
+              const int e = nn - a.N0;
+              grow[e] = fmaf(a.g_scale * __ldg(a.Cy + (long long)m * a.n + e), acc, grow[e]);
+            }
+          }
+        }
+      }
+      cg::this_cluster().sync();   // partial tiles stay alive until every rank has read them
+    } else
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= a.N) break;          // warp-uniform: whole chunk out of range
       uint32_t v[32], w[32];
@@ -363,6 +433,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
     tc_fence_before();
   }
+  if (S > 1 && warp < 2) { cg::this_cluster().sync(); cg::this_cluster().sync(); }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -459,7 +530,7 @@ static int make_tmap(CUtensorMap* tm, const float* base, long long rows, long lo
 
 template <int BN, int NST_>
 static cudaError_t launch_tc_variant(const CUtensorMap& tAh, const CUtensorMap& tAl, const CUtensorMap& tBh,
-                                     const CUtensorMap& tBl, const TcArgs& a, cudaStream_t st) {
+                                     const CUtensorMap& tBl, const TcArgs& a, int splitk, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, NST_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -467,9 +538,16 @@ static cudaError_t launch_tc_variant(const CUtensorMap& tAh, const CUtensorMap& 
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  dim3 grid(cdiv(a.N, BN), cdiv(a.M, TC_BM));
-  tc_gemm_kernel<BN, NST_><<<grid, 192, TcSmem<BN, NST_>::TOTAL, st>>>(tAh, tAl, tBh, tBl, a);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cdiv(a.N, BN), cdiv(a.M, TC_BM), splitk);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = TcSmem<BN, NST_>::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute lattr[1];
+  lattr[0].id = cudaLaunchAttributeClusterDimension;
+  lattr[0].val.clusterDim.x = 1; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = splitk;
+  cfg.attrs = lattr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, NST_>, tAh, tAl, tBh, tBl, a);
 }
 
 static int launch_tc_gemm(const float* Ah, const float* Al, long long lda, const float* Bh, const float* Bl, long long ldb,
@@ -491,9 +569,16 @@ static int launch_tc_gemm(const float* Ah, const float* Al, long long lda, const
   if ((rc = make_tmap(&tAl, Al, a.M, a.K, lda, TC_BM))) return rc;
   if ((rc = make_tmap(&tBh, Bh, a.N, a.K, ldb, BN))) return rc;
   if ((rc = make_tmap(&tBl, Bl, a.N, a.K, ldb, BN))) return rc;
-  cudaError_t e = cfg == 0 ? launch_tc_variant<128, 3>(tAh, tAl, tBh, tBl, a, st)
-                : cfg == 1 ? launch_tc_variant<64, 4>(tAh, tAl, tBh, tBl, a, st)
-                           : launch_tc_variant<64, 2>(tAh, tAl, tBh, tBl, a, st);
+  // split-K over a cluster when the tile grid leaves most of the chip idle (C2: 4 row tiles)
+  int splitk = 1;
+  if (cfg == 1 && (a.mode == 0 || a.mode == 1)) {
+    const int tiles = cdiv(a.N, 64) * gy, nkb = cdiv(a.K, TC_BK);
+    while (splitk < 8 && tiles * splitk * 2 <= 148 && nkb / (splitk * 2) >= 4) splitk *= 2;
+    if (const char* v = getenv("ICNN_TC_SPLITK")) { const int w = atoi(v); if (w == 1 || w == 2 || w == 4 || w == 8) splitk = w; }
+  }
+  cudaError_t e = cfg == 0 ? launch_tc_variant<128, 3>(tAh, tAl, tBh, tBl, a, 1, st)
+                : cfg == 1 ? launch_tc_variant<64, 4>(tAh, tAl, tBh, tBl, a, splitk, st)
+                           : launch_tc_variant<64, 2>(tAh, tAl, tBh, tBl, a, 1, st);
   if (e != cudaSuccess) { set_error("tc_gemm launch: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
   return ICNN_OK;
 }
