@@ -176,24 +176,15 @@ __device__ inline bool warp_cholesky(double* A, double* invd, int k, int ld, int
   bool ok = true;
   const int r0 = lane, r1 = lane + 32;
   for (int c = 0; c < k; ++c) {
-    // four independent partial sums per row: the loads are independent, the FMA chain is not
-    auto rowdot = [&](int r) {
-      const double* ar = A + r * ld;
-      const double* ac = A + c * ld;
-      double a0 = ar[c], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int p = 0;
-      for (; p + 3 < c; p += 4) {
-        a0 = fma(-ar[p], ac[p], a0);
-        a1 = fma(-ar[p + 1], ac[p + 1], a1);
-        a2 = fma(-ar[p + 2], ac[p + 2], a2);
-        a3 = fma(-ar[p + 3], ac[p + 3], a3);
-      }
-      for (; p < c; ++p) a0 = fma(-ar[p], ac[p], a0);
-      return (a0 + a1) + (a2 + a3);
-    };
     double s0 = 0.0, s1 = 0.0;
-    if (r0 >= c && r0 < k) s0 = rowdot(r0);
-    if (r1 >= c && r1 < k) s1 = rowdot(r1);
+    if (r0 >= c && r0 < k) {
+      s0 = A[r0 * ld + c];
+      for (int p = 0; p < c; ++p) s0 = fma(-A[r0 * ld + p], A[c * ld + p], s0);
+    }
+    if (r1 >= c && r1 < k) {
+      s1 = A[r1 * ld + c];
+      for (int p = 0; p < c; ++p) s1 = fma(-A[r1 * ld + p], A[c * ld + p], s1);
+    }
     const double piv = __shfl_sync(0xffffffffu, (c < 32) ? s0 : s1, c & 31);
     if (!(piv > 0.0) || !isfinite(piv)) { ok = false; break; }
     const double inv = rsqrt(piv);
@@ -739,12 +730,6 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
         g.cvsum(M, k * ld, rdk, 2 * KS, sc + 11, 1);
         pr = sc[11];
       }
-      // Lm = M + diag(s / z), built by the whole group (the factorisation itself runs on warp 0)
-      for (int idx = g.tid; idx < k * k; idx += T) {
-        const int i = idx / k, j = idx - i * k;
-        Lm[i * ld + j] = M[i * ld + j] + (i == j ? sk[i] / zk[i] : 0.0);
-      }
-      g.sync();
       if (g.warp == 0) {
         const int lane = g.lane;
         for (int j = lane; j < k; j += 32) rdk[j] = ((rdk[j] + hk[j]) - sc[0]) + sk[j];   // rd = G y + h - t + s
@@ -758,6 +743,11 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
         if (conv) {
           if (lane == 0) isc[2] = 1;
         } else {
+          for (int i = lane; i < k; i += 32) {
+            for (int j = 0; j < k; ++j) Lm[i * ld + j] = M[i * ld + j];
+            Lm[i * ld + i] += sk[i] / zk[i];
+          }
+          __syncwarp();
           const bool ok = warp_cholesky(Lm, invd, k, ld, lane);
           if (!ok) { if (lane == 0) isc[3] = 1; }
           else {
