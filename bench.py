@@ -341,8 +341,10 @@ def run_gpu(args):
                    peak=peaks["hbm_gbs"], unit="GB/s", traffic=None, launches=its,
                    ms_per_launch=k2_ms / max(its, 1), share_of_step=k2_ms / (k1_ms + k2_ms))
     roof_k2["frac"] = roof_k2["achieved"] / roof_k2["peak"]
-    k1_name = ("tc_gemm_kernel (tcgen05 3xTF32 + TMA) + gate_y + out_layer" if int(os.environ.get("ICNN_K1", "t")[0] != "s")
-               and n % 4 == 0 and all(hh % 4 == 0 for hh in cfg["hidden"]) else "gated_gemm_kernel + out_layer (FP32 FFMA)")
+    tc_shape = n % 4 == 0 and all(hh % 4 == 0 for hh in cfg["hidden"]) and B >= 64
+    tc_on = tc_shape and not os.environ.get("ICNN_K1", "tc").startswith("s")
+    k1_name = ("tc_gemm_kernel (tcgen05 3xTF32 + TMA) + gate_y + out_layer" if tc_on
+               else "gated_gemm_kernel + out_layer (FP32 FFMA)")
     roof_k1 = dict(kernel=k1_name, bound="tensor",
                    achieved=k1_flops / (k1_ms * 1e-3) / 1e12, peak=peaks["bf16_sustained"], unit="TFLOP/s",
                    traffic=None, launches=its * (2 * len(cfg["hidden"]) + 2),

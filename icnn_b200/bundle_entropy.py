@@ -174,7 +174,7 @@ def solveBatch(fg, initXs, nIter=None, callback=None, solver="pc", *, variant="l
     dev = fg.net.device if fused else torch.device(device if device is not None else "cuda")
     x0 = initXs
     B, n = x0.shape
-    if nIter < 1:
+    if B == 0 or nIter < 1:
         return (_to_numpy(x0), [[] for _ in range(B)], [[] for _ in range(B)], [None] * B,
                 [[] for _ in range(B)], [nIter] * B)
     # slot capacity: active rows <= min(nIter, n) for the rank-tested copies, + 1 free slot

@@ -9,8 +9,6 @@
 
 namespace icnn {
 
-struct StepArgs;  // defined in bundle_step.cu; re-declared layout-compatible subset below
-
 struct SmallArgs {
   icnn_bundle_bufs b;
   icnn_bundle_cfg c;

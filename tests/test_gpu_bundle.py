@@ -235,6 +235,9 @@ def test_edge_cases_and_error_paths():
     r = be.solveBatch(fg, y0.copy(), nIter=1)
     o = bundle_np.solve_batch(picnn_np.make_fg(p, x), y0.copy(), nIter=1)
     assert rowdiff(r[0], o[0]).max() < 1e-5 and r[5] == o[5]
+    # empty batch: the reference's loops simply do nothing
+    e = be.solveBatch(lambda yy: (np.zeros(0), np.zeros((0, 8))), np.zeros((0, 8)), nIter=3)
+    assert e[0].shape == (0, 8) and len(e[1]) == 0 and e[5] == []
     # B = 1
     r1 = be.solveBatch(net.bind(x[:1]), y0[:1].copy(), nIter=5)
     # (the x-path gates come from cuBLAS, which is not batch-invariant -> float32-level noise)
