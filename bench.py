@@ -341,6 +341,12 @@ def run_gpu(args):
                    peak=peaks["hbm_gbs"], unit="GB/s", traffic=None, launches=its,
                    ms_per_launch=k2_ms / max(its, 1), share_of_step=k2_ms / (k1_ms + k2_ms))
     roof_k2["frac"] = roof_k2["achieved"] / roof_k2["peak"]
+    if args.workload == "C2":
+        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+        # (profiles/r01_c2_summary.md section 3: outer iteration t = 20, k ~ 19 rows; the algorithmic
+        # bytes of that launch are 69 MB)
+        roof_k2["traffic"] = 72.18e6 + 9.43e6
+        roof_k2["traffic_source"] = "ncu capture at t=20 (profiles/r01_c2_summary.md); per-launch, bytes"
     tc_shape = n % 4 == 0 and all(hh % 4 == 0 for hh in cfg["hidden"]) and B >= 64
     tc_on = tc_shape and not os.environ.get("ICNN_K1", "tc").startswith("s")
     k1_name = ("tc_gemm_kernel (tcgen05 3xTF32 + TMA) + gate_y + out_layer" if tc_on

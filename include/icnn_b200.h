@@ -79,7 +79,7 @@ typedef struct {
  * perm[u, 0..count[u]) lists the active slots in the reference's list order and
  * perm[u, count[u]] is the free slot the next gradient row is written to. */
 typedef struct {
-  int32_t B, n, KS;  /* KS = slot capacity >= max active rows + 1                      */
+  int32_t B, n, KS;  /* KS = slot capacity >= max active rows + 1 (<= 64: nIter <= 63)    */
   double* y;         /* [B, n]      iterate (float64, like the reference's x)          */
   float* y32;        /* [B, n]      iterate rounded for the fg kernel                  */
   float* f;          /* [B]         f(y) of the current iterate                        */
