@@ -67,8 +67,11 @@ def _cpu_worker(args):
     cfg = workloads.CONFIGS[workload]
     p, x, y0 = workloads.make_inputs(workload, B=Bgen, seed=seed)
     x, y0 = x[lo:hi], y0[lo:hi].copy()
-    # float32 arithmetic + float32 fetch mimics the reference's TF-backed fg
-    fg = picnn_np.make_fg(p, x, dtype=np.float32, out_dtype=np.float32, affine=cfg["affine"])
+    # float32 arithmetic mimics the reference's TF-backed fg; the values are handed over in float64
+    # arrays so that the CPU arm does the same work as the GPU arm: np.linalg.matrix_rank scales its
+    # tolerance with the row dtype, and with float32-typed rows most samples hit the rank stop early
+    # (they would still be counted as "solves" while doing nothing)
+    fg = picnn_np.make_fg(p, x, dtype=np.float32, out_dtype=np.float64, affine=cfg["affine"])
     iters = [0]
 
     def cb(t, *a):
@@ -153,7 +156,7 @@ def cpu_baseline(workload, budget_s=15.0):
         solves, wall, rows = s0, w0, cal_rows
     return dict(value=solves / wall, unit=UNIT, cores=min(procs, rows), kind="port",
                 sample="%d of %d rows x %d iterations requested (%d solves executed, %.1f s wall), "
-                       "numpy oracle port of lib/bundle_entropy.solveBatch(solver='pc'), float32 fg, "
+                       "numpy oracle port of lib/bundle_entropy.solveBatch(solver='pc'), float32-arithmetic fg, "
                        "%d processes x 1 BLAS thread" % (rows, cfg["B"], cfg["nIter"], solves, wall,
                                                          min(procs, rows)))
 
@@ -446,7 +449,7 @@ def run_reference(args):
         tot_w += w
     value = tot_s / tot_w
     sample = ("%d of %d rows x nIter=%d per step, numpy oracle port of lib/bundle_entropy.solveBatch"
-              "(solver='pc') with float32 fg, %d processes x 1 BLAS thread" % (rows, cfg["B"], cfg["nIter"],
+              "(solver='pc') with float32-arithmetic fg, %d processes x 1 BLAS thread" % (rows, cfg["B"], cfg["nIter"],
                                                                               min(procs, rows)))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": tot_w / args.steps * 1e3, "higher_is_better": True,

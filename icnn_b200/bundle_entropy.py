@@ -143,6 +143,12 @@ def _make_cfg(variant, solver, nIter, line_search, rank_tol, max_inner, n, KS):
                            float(rank_tol), int(nIter), 0)
 
 
+def _dtype_of(a):
+    if isinstance(a, torch.Tensor):
+        return {torch.float32: np.float32, torch.float64: np.float64}.get(a.dtype, None)
+    return np.asarray(a).dtype.type
+
+
 def _to_numpy(a):
     if isinstance(a, torch.Tensor):
         return a.detach().cpu().numpy()
@@ -211,6 +217,10 @@ def solveBatch(fg, initXs, nIter=None, callback=None, solver="pc", *, variant="l
                 else:
                     xi = st.y.cpu().numpy()
                     fi, gi = fg(xi)
+                    if t == 0 and rank_tol is None and variant != "rl" and _dtype_of(gi) == np.float32:
+                        # np.linalg.matrix_rank scales its tolerance with the dtype of the rows: a
+                        # float32 fg (the reference's TF fetch) stops samples at max(k, n) * eps32
+                        cfg.rank_tol = float(max(KS, n) * np.finfo(np.float32).eps)
                     if callback is not None:
                         if variant == "rl":
                             callback(t, _to_numpy(fi))
