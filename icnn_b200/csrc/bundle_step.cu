@@ -711,17 +711,30 @@ __global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
       if (WPS == 1) __syncwarp();
       // row pass (rd = G y + h - t + s ; q = G D ry) on the upper half of the group's warps while
       // the lower half sweeps the weighted Gram on the FP64 tensor cores (both only read G, y, D, ry)
-      for (int j = (WPS == 1 ? 0 : g.warp - NWG); j < k && j >= 0; j += (WPS == 1 ? 1 : WPS - NWG)) {
-        const float* rj = rowp[j];
-        double a1 = 0.0, a2 = 0.0;
-        for (int e = g.lane; e < n; e += 32) {
-          const double ge = (double)ldf(rj + e);
-          a1 = fma(ge, yv[e], a1);
-          a2 = fma(ge, dv[e] * rv[e], a2);
+      // Rows are taken four at a time per warp: four independent loads per element (the loop is
+      // L2-latency bound) and one read of y, D, ry for the four rows.
+      {
+        const int rw = (WPS == 1) ? 0 : g.warp - NWG, nrw = (WPS == 1) ? 1 : WPS - NWG;
+        for (int j0 = 4 * rw; j0 < k && rw >= 0; j0 += 4 * nrw) {
+          const float* rj[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) rj[r] = rowp[::min(j0 + r, k - 1)];
+          double a1[4] = {0.0, 0.0, 0.0, 0.0}, a2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+          for (int e = g.lane; e < n; e += 32) {
+            float gv[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) gv[r] = ldf(rj[r] + e);
+            const double ye = yv[e], te = dv[e] * rv[e];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { a1[r] = fma((double)gv[r], ye, a1[r]); a2[r] = fma((double)gv[r], te, a2[r]); }
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const double s1 = Grp<WPS>::wsum(a1[r]), s2 = Grp<WPS>::wsum(a2[r]);
+            if (g.lane == 0 && j0 + r < k) { rdk[j0 + r] = s1; qk[j0 + r] = s2; }   // column sums only; h - t + s is added below
+          }
         }
-        a1 = Grp<WPS>::wsum(a1);
-        a2 = Grp<WPS>::wsum(a2);
-        if (g.lane == 0) { rdk[j] = a1; qk[j] = a2; }   // column sums only; h - t + s is added below
       }
       gram_pass<WPS>(g, rowp, k, n, dv, M, ld, WIDX, NWG);
       g.sync();
