@@ -229,9 +229,19 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     cfg = workloads.CONFIGS[args.workload]
     B, n, nIter = cfg["B"], cfg["n"], cfg["nIter"]
-    # weak scaling: every rank solves its own B rows (different seed -> different rows)
-    p, x, y0 = workloads.make_inputs(args.workload, seed=cfg["seed"] + 7919 * rank)
-    p0 = workloads.make_inputs(args.workload, B=1)[0] if rank else p   # theta replicated = rank 0's
+    strong = (args.scaling == "strong")
+    if strong:
+        # strong scaling: the workload's B rows are sharded over the ranks (contiguous blocks,
+        # icnn_b200/dist.py) -- e.g. C4: 65 536 replay samples over 8 GPUs (BASELINE.json configs[3])
+        p, x_all, y0_all = workloads.make_inputs(args.workload)
+        lo, hi = idist.shard_rows(B, rank, world)
+        x, y0 = x_all[lo:hi], y0_all[lo:hi]
+        Btot, B = B, hi - lo
+        p0 = p
+    else:
+        # weak scaling: every rank solves its own B rows (different seed -> different rows)
+        p, x, y0 = workloads.make_inputs(args.workload, seed=cfg["seed"] + 7919 * rank)
+        p0 = workloads.make_inputs(args.workload, B=1)[0] if rank else p   # theta replicated = rank 0's
     net = icnn_b200.PICNN.from_params(p0, device=dev)
     x_pin = torch.from_numpy(x.astype(np.float32)).pin_memory()
     y0_pin = torch.from_numpy(y0).pin_memory()
@@ -240,8 +250,14 @@ def run_gpu(args):
     ccfg = bundle_entropy._make_cfg(variant, solver, nIter, None, None, 0, n, KS)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    Bglob = B * world
+    Bglob = Btot if strong else B * world
     y_all = torch.empty(Bglob, n, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def gather(y_local):
+        if strong:
+            y_all.copy_(idist.allgather_rows(y_local, Bglob))
+        else:
+            dist.all_gather_into_tensor(y_all, y_local)
 
     # ---- device-resident step -----------------------------------------------------------------
     fg = net.bind(x_pin.to(dev), affine=cfg["affine"])
@@ -253,7 +269,7 @@ def run_gpu(args):
         _capi.check(_capi.lib.icnn_solve_batch_fused(net._h, C.byref(fg.c_gates), C.byref(ccfg), C.byref(st.c),
                                                      fg.ws.data_ptr(), stream))
         if world > 1:
-            dist.all_gather_into_tensor(y_all, st.y)
+            gather(st.y)
 
     def iters_executed():
         na = st.nactive.cpu().numpy()
@@ -268,6 +284,10 @@ def run_gpu(args):
         step_device()
     barrier()
     its = iters_executed()
+    if world > 1:   # a job-level count: the slowest rank's shard decides when the loop is over
+        t_its = torch.tensor([its], dtype=torch.int64, device=dev)
+        dist.all_reduce(t_its, op=dist.ReduceOp.MAX)
+        its = int(t_its.item())
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with ClockSampler(local) as clk:
         barrier()
@@ -293,7 +313,7 @@ def run_gpu(args):
         out = bundle_entropy.solveBatch(fg_h, y0_pin, nIter=nIter, solver=solver,
                                         variant=variant, return_state=True)   # H2D y0 (pinned) ... D2H y*
         if world > 1:
-            dist.all_gather_into_tensor(y_all, out[-1].y)
+            gather(out[-1].y)
         return out
 
     for _ in range(2):
@@ -405,7 +425,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (K1 PICNN f/grad) + f64 (K2 bundle solve)",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 (K1 PICNN f/grad) + f64 (K2 bundle solve)",
             "data": "synthetic", "impl": "icnn_b200",
             "config": {"workload": "%s: m=%d n_y=%d hidden=%s batch=%d/GPU nIter=%d variant=%s solver=%s"
                                    % (args.workload, cfg["m"], n, cfg["hidden"], B, nIter, variant, solver),
@@ -473,6 +493,8 @@ def main():
     ap.add_argument("--impl", default="icnn_b200", choices=["icnn_b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5", "T"])
     ap.add_argument("--solver", default="pc", choices=["pc", "newton"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's batch per GPU (default); strong: the batch sharded over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-target-shape", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
