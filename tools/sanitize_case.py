@@ -1,0 +1,36 @@
+"""Small end-to-end cases for compute-sanitizer (memcheck / racecheck / synccheck):
+    compute-sanitizer --tool racecheck python tools/sanitize_case.py
+Covers K1 FFMA + cluster split-K, K1 tcgen05 path, K2 group kernel (WPS 1/2/8, PC + dual + RL Newton),
+K2 thread-per-sample kernel, K3, Adam, x-path gates."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import icnn_b200
+from icnn_b200 import bundle_entropy as be, workloads
+
+def run(name, B, nIter, variant=None, **kw):
+    cfg = workloads.CONFIGS[name]
+    p, x, y0 = workloads.make_inputs(name, B=B)
+    net = icnn_b200.PICNN.from_params(p)
+    fg = net.bind(x, affine=cfg["affine"])
+    out = be.solveBatch(fg, y0.copy(), nIter=nIter, variant=variant or cfg["variant"], return_state=True, **kw)
+    print(name, B, nIter, variant or cfg["variant"], "ok, y range", float(out[0].min()), float(out[0].max()), flush=True)
+    return net, fg, out
+
+which = sys.argv[1:] or ["c1", "c3", "c3dual", "c4", "c2", "t", "k3", "adam"]
+if "c1" in which: run("C1", 16, 4)
+if "c3" in which: run("C3", 6, 4)
+if "c3dual" in which: run("C3", 6, 4, variant="dual")
+if "c4" in which:
+    run("C4", 40, 4)
+    os.environ["ICNN_K2_SMALL"] = "0"; run("C4", 16, 3); os.environ.pop("ICNN_K2_SMALL")
+if "c2" in which: run("C2", 2, 4)
+if "t" in which: run("T", 64, 2)
+if "k3" in which:
+    net, fg, out = run("C3", 6, 4)
+    tY = (np.random.RandomState(0).uniform(size=out[0].shape) < 0.3).astype(np.float64)
+    icnn_b200.argmin_grad.argmin_grad(out[-1], tY, loss="xent"); print("k3 ok", flush=True)
+if "adam" in which:
+    p, x, _ = workloads.make_inputs("C4", B=8)
+    a, its = icnn_b200.adam.solve(icnn_b200.PICNN.from_params(p).bind(x), max_iter=24, return_iters=True); print("adam ok", its, flush=True)
+print("done")
