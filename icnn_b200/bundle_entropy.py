@@ -27,7 +27,7 @@ import torch
 from . import _capi
 from .picnn import BoundPICNN
 
-__all__ = ["solveBatch", "BundleState", "VARIANT_DEFAULTS"]
+__all__ = ["solveBatch", "solve", "BundleState", "VARIANT_DEFAULTS"]
 
 # reference defaults per copy: (nIter, solver, line_search, prune_thr)
 VARIANT_DEFAULTS = {
@@ -249,3 +249,18 @@ def solveBatch(fg, initXs, nIter=None, callback=None, solver="pc", *, variant="l
     if return_state:
         return out + (st,)
     return out
+
+
+def solve(fg, initX, nIter=10, callback=None, *, variant="dual", **kw):
+    """Single-sample form of the reference (lib/bundle_entropy_dual.py:87-127 ``solve``; the
+    ``solve`` of lib/bundle_entropy.py:168-190 is dead code there): ``fg(x [n]) -> (f, g [n])``,
+    returns the final iterate.  Runs as a batch of one through :func:`solveBatch`."""
+    x0 = np.array(initX, dtype=np.float64).reshape(1, -1)
+
+    def fg1(xb):
+        f, g = fg(xb[0])
+        return np.atleast_1d(np.asarray(f, dtype=np.float64)), np.asarray(g, dtype=np.float64).reshape(1, -1)
+
+    cb = None if callback is None else (lambda t, f, x=None: callback(t, f[0], None if x is None else x[0]))
+    out = solveBatch(fg1, x0, nIter=nIter, callback=cb, variant=variant, **kw)
+    return out[0][0]

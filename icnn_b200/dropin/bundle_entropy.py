@@ -16,3 +16,7 @@ from icnn_b200 import bundle_entropy as _be  # noqa: E402
 
 def solveBatch(fg, initXs, nIter=10, callback=None, solver='pc', **kw):
     return _be.solveBatch(fg, initXs, nIter=nIter, callback=callback, solver=solver, variant='lib', **kw)
+
+
+def solve(fg, initX, nIter=10, callback=None, **kw):
+    return _be.solve(fg, initX, nIter=nIter, callback=callback, variant='lib', **kw)

@@ -324,3 +324,16 @@ def test_callback_mode_mirrors_numpy_rank_tolerance_dtype():
     assert np.mean(np.abs(np.array(r[5]) - np.array(o[5])) <= 2) >= 0.6, (r[5], o[5])
     assert np.median(rowdiff(r[0], o[0])) < 1e-4
     assert max(r[5]) <= max(o[5]) + 2 and min(r[5]) < 30            # early stops do happen
+
+
+def test_single_sample_solve_alias():
+    """lib/bundle_entropy_dual.py:87-127 `solve`: one sample, fg(x [n]) -> (f, g [n])."""
+    from icnn_b200 import bundle_entropy as be
+    p, x, y0 = synth.make_inputs("C3", B=1)
+    fgb = picnn_np.make_fg(p, x)
+    fg1 = lambda y: tuple(v[0] for v in fgb(y[None, :]))  # noqa: E731
+    seen = []
+    xs = be.solve(fg1, y0[0], nIter=6, callback=lambda t, f, xx: seen.append(t))
+    o = bundle_np.solve_batch(fgb, y0.copy(), nIter=6, variant="dual")
+    assert xs.shape == (159,) and seen == list(range(len(seen))) and len(seen) >= 1
+    assert np.abs(xs - o[0][0]).max() < 1e-5
