@@ -232,11 +232,8 @@ def solveBatch(fg, initXs, nIter=None, callback=None, solver="pc", *, variant="l
                 _capi.check(_capi.lib.icnn_bundle_step(C.byref(cfg), C.byref(st.c), t, stream))
                 if int(st.nactive[t + 1].item()) == 0:   # lib/bundle_entropy.py:239
                     break
-        # D2H of y* through pinned memory (torch caches the pinned block between calls)
-        y_host = torch.empty((B, n), dtype=torch.float64, pin_memory=True)
-        y_host.copy_(st.y, non_blocking=True)
-        status = st.status.cpu().numpy()          # synchronises the stream: y_host is complete
-        x = y_host.numpy()
+        x = st.y.cpu().numpy()
+        status = st.status.cpu().numpy()
     if np.any(status == _capi.ST_NONFINITE) or np.any(status == _capi.ST_SOLVE_FAIL):
         msg = "solveBatch: %d samples non-finite, %d with a failed inner solve" % (
             int(np.sum(status == _capi.ST_NONFINITE)), int(np.sum(status == _capi.ST_SOLVE_FAIL)))
