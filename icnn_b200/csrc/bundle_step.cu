@@ -1265,7 +1265,7 @@ __global__ void put_fg_kernel(icnn_bundle_bufs b, const float* f, const float* g
 
 // Launch configuration: warps per sample (WPS), cluster size over columns (CS) and whether the
 // sample's rows are kept resident in shared memory.
-//   n <= 128: 1 warp / sample, <= 512: 2, <= 1024: 4, else 8 (one CTA per column slice);
+//   n <= 192: 1 warp / sample, <= 512: 2, <= 1024: 4, else 8 (one CTA per column slice);
 //   resident rows whenever KS x slice fits next to the work vectors; the sample is split over
 //   CS = 2/4/8 CTAs of a cluster when one CTA cannot hold it (or to get two CTAs per SM).
 struct K2Config { int wps, cs, nloc, gpitch, npad, ld; size_t smem; };
@@ -1287,7 +1287,9 @@ static bool k2_fits(const icnn_bundle_bufs* b, int wps, int cs, bool resident, s
 
 static int pick_k2(const icnn_bundle_bufs* b, K2Config* out) {
   const int n = b->n;
-  int wps = n <= 128 ? 1 : (n <= 512 ? 2 : (n <= 1024 ? 4 : 8));
+  // measured (K2 ms per solveBatch): n=159 (C3) WPS 1: 6.8, 2: 7.9;  n=512 (T) 1: 12.8, 2: 9.3, 4: 12.9;
+  // n=2048 (C2) 4: 41.7, 8: 19.4
+  int wps = n <= 192 ? 1 : (n <= 512 ? 2 : (n <= 1024 ? 4 : 8));
   if (const char* v = getenv("ICNN_K2_WPS")) { const int w = atoi(v); if (w == 1 || w == 2 || w == 4 || w == 8) wps = w; }
   int want_cs = 0;
   if (const char* v = getenv("ICNN_K2_CS")) want_cs = atoi(v);
