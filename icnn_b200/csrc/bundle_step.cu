@@ -113,7 +113,7 @@ struct Grp {
 
   __device__ __forceinline__ void sync() const {
     if (WPS == 1) __syncwarp();
-    else if (WPS == 8) __syncthreads();
+    else if (WPS >= 8) __syncthreads();      // the group is the whole CTA (256 or 512 threads)
     else asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(WPS * 32) : "memory");
   }
   static __device__ __forceinline__ double wsum(double v) {
@@ -470,13 +470,15 @@ __device__ inline void gram_pass(const G& g, const float* const* rowp, int k, in
 // CTA keeps its column slice of the bundle rows RESIDENT in shared memory (A.gpitch > 0), runs
 // the column / row / Gram passes on its slice and exchanges the partial sums through distributed
 // shared memory; the k x k algebra is replicated in every CTA.
+// WPS == 16: one 512-thread CTA per sample, for n_y so large that shared memory allows a single CTA
+// per SM anyway (C5: n_y = 4096) -- twice the threads on the passes.
 template <int WPS, int MINB, int CS>
-__global__ void __launch_bounds__(256, MINB) bundle_step_kernel(StepArgs A) {
+__global__ void __launch_bounds__(WPS == 16 ? 512 : 256, MINB) bundle_step_kernel(StepArgs A) {
   const icnn_bundle_bufs& b = A.b;
   const icnn_bundle_cfg& cf = A.c;
   if (b.nactive[A.t] == 0) return;
   extern __shared__ __align__(16) double smem_d[];
-  constexpr int GPB = 8 / WPS;  // groups per block
+  constexpr int GPB = (WPS >= 8) ? 1 : 8 / WPS;  // groups per block
   constexpr int T = WPS * 32;
   static_assert(CS == 1 || WPS == 8, "a cluster-split sample owns whole CTAs");
   Grp<WPS, CS> g;
@@ -1279,7 +1281,7 @@ static bool k2_fits(const icnn_bundle_bufs* b, int wps, int cs, bool resident, s
   c.ld = b->KS | 1;
   c.gpitch = 0;
   if (resident) { const int p4 = (c.nloc + 3) & ~3; c.gpitch = p4 + ((16 - (p4 & 31)) & 31); }   // = 16 mod 32 floats
-  c.smem = sizeof(double) * group_smem_doubles(c.npad, b->KS, c.ld, wps, c.gpitch, cs) * (8 / wps);
+  c.smem = sizeof(double) * group_smem_doubles(c.npad, b->KS, c.ld, wps, c.gpitch, cs) * (wps >= 8 ? 1 : 8 / wps);
   if (c.smem > limit) return false;
   *out = c;
   return true;
@@ -1290,7 +1292,11 @@ static int pick_k2(const icnn_bundle_bufs* b, K2Config* out) {
   // measured (K2 ms per solveBatch): n=159 (C3) WPS 1: 6.8, 2: 7.9;  n=512 (T) 1: 12.8, 2: 9.3, 4: 12.9;
   // n=2048 (C2) 4: 41.7, 8: 19.4
   int wps = n <= 192 ? 1 : (n <= 512 ? 2 : (n <= 1024 ? 4 : 8));
-  if (const char* v = getenv("ICNN_K2_WPS")) { const int w = atoi(v); if (w == 1 || w == 2 || w == 4 || w == 8) wps = w; }
+  if (const char* v = getenv("ICNN_K2_WPS")) { const int w = atoi(v); if (w == 1 || w == 2 || w == 4 || w == 8 || w == 16) wps = w; }
+  else if (wps == 8) {   // a single CTA per SM fits anyway -> give the sample 16 warps
+    K2Config probe;
+    if (k2_fits(b, 8, 1, false, 227 * 1024, &probe) && probe.smem > 113 * 1024) wps = 16;
+  }
   int want_cs = 0;
   if (const char* v = getenv("ICNN_K2_CS")) want_cs = atoi(v);
   // Resident rows / cluster split are OFF by default: measured on B200 (round 1) they lose to
@@ -1322,13 +1328,14 @@ static int pick_k2(const icnn_bundle_bufs* b, K2Config* out) {
 template <int WPS, int CS>
 static cudaError_t launch_k2(const StepArgs& a, const K2Config& c, int B, cudaStream_t st) {
   // 3 CTAs / SM (80 registers) when the shared-memory footprint allows it, else the 128-register build
-  const bool three = c.smem * 3 <= 225 * 1024;
-  void (*kern)(StepArgs) = three ? bundle_step_kernel<WPS, 3, CS> : bundle_step_kernel<WPS, 2, CS>;
+  const bool three = (WPS != 16) && c.smem * 3 <= 225 * 1024;
+  void (*kern)(StepArgs) = three ? bundle_step_kernel<WPS, (WPS == 16 ? 1 : 3), CS>
+                                 : bundle_step_kernel<WPS, (WPS == 16 ? 1 : 2), CS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(CS == 1 ? cdiv(B, 8 / WPS) : B * CS));
-  cfg.blockDim = dim3(256);
+  cfg.gridDim = dim3((unsigned)(CS == 1 ? cdiv(B, WPS >= 8 ? 1 : 8 / WPS) : B * CS));
+  cfg.blockDim = dim3(WPS == 16 ? 512 : 256);
   cfg.dynamicSmemBytes = c.smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1360,6 +1367,7 @@ int bundle_step_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, in
   else if (c.wps == 1) e = launch_k2<1, 1>(a, c, b->B, st);
   else if (c.wps == 2) e = launch_k2<2, 1>(a, c, b->B, st);
   else if (c.wps == 4) e = launch_k2<4, 1>(a, c, b->B, st);
+  else if (c.wps == 16) e = launch_k2<16, 1>(a, c, b->B, st);
   else e = launch_k2<8, 1>(a, c, b->B, st);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("bundle_step launch (wps=%d cs=%d smem=%zu): %s", c.wps, c.cs, c.smem, cudaGetErrorString(e)); return ICNN_E_CUDA; }

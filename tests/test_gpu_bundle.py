@@ -279,11 +279,13 @@ def test_early_exit_when_all_finished():
                                               ("C2", 5, 12, {"ICNN_K2_RESIDENT": "1", "ICNN_K2_CS": "2"}),
                                               ("T", 20, 10, {"ICNN_K2_RESIDENT": "1"}),
                                               ("C3", 20, 10, {"ICNN_K2_RESIDENT": "1"}),
-                                              ("C5", 3, 12, {"ICNN_K2_RESIDENT": "1", "ICNN_K2_CS": "8"})])
+                                              ("C5", 3, 12, {"ICNN_K2_RESIDENT": "1", "ICNN_K2_CS": "8"}),
+                                              ("C5", 3, 12, {"ICNN_K2_WPS": "16"}),      # 512-thread CTA per sample
+                                              ("C2", 5, 12, {"ICNN_K2_WPS": "16"})])
 def test_resident_cluster_variant_matches_streaming(name, B, nIter, env, monkeypatch):
-    """The optional K2 variant (rows resident in shared memory, sample split over a thread-block
-    cluster with DSMEM exchanges) computes the same thing as the default streaming kernel.  The
-    launch configuration is read from the environment at every launch."""
+    """The optional K2 launch variants (rows resident in shared memory, sample split over a
+    thread-block cluster with DSMEM exchanges, 16 warps per sample) compute the same thing as the
+    default streaming kernel.  The launch configuration is read from the environment at every launch."""
     from icnn_b200 import bundle_entropy as be
     p, x, y0 = synth.make_inputs(name, B=B)
     fg = r32(picnn_np.make_fg(p, x))
