@@ -28,6 +28,7 @@ SYMBOLS = [
     "icnn_solve_batch_fused", "icnn_gd_solve", "icnn_tc_gemm_selftest", "icnn_argmin_grad",
     "icnn_picnn_set_xpath", "icnn_picnn_gates_workspace_bytes", "icnn_picnn_gates",
     "icnn_adam_workspace_bytes", "icnn_adam_solve",
+    "icnn_gd_backward_workspace_bytes", "icnn_gd_backward",
 ]
 
 _fpp = C.POINTER(C.c_void_p)
@@ -56,6 +57,10 @@ class BundleCfg(C.Structure):
     _fields_ = [("variant", C.c_int32), ("solver", C.c_int32), ("line_search", C.c_int32),
                 ("max_inner", C.c_int32), ("prune_thr", C.c_double), ("rank_tol", C.c_double),
                 ("nIter", C.c_int32), ("reserved", C.c_int32)]
+
+
+class GdGrads(C.Structure):
+    _fields_ = [("dWy", _fpp), ("dWz", _fpp), ("dcy", _fpp), ("dcz", _fpp)]
 
 
 class IcnnError(RuntimeError):
@@ -97,6 +102,10 @@ def _load():
                                     C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.icnn_argmin_grad.argtypes = [C.POINTER(BundleBufs), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.icnn_gd_backward_workspace_bytes.argtypes = [C.c_void_p, C.c_int32]
+    lib.icnn_gd_backward_workspace_bytes.restype = C.c_size_t
+    lib.icnn_gd_backward.argtypes = [C.c_void_p, C.POINTER(Gates), C.c_void_p, C.c_void_p, C.c_float, C.c_int32,
+                                     C.c_float, C.c_float, C.c_void_p, C.POINTER(GdGrads), C.c_void_p, C.c_void_p]
     for name in SYMBOLS:
         getattr(lib, name)  # AttributeError if the .so does not export it
     if lib.icnn_abi_version() != ABI_VERSION:

@@ -1,0 +1,347 @@
+// d loss / d theta through the unrolled momentum-GD inner loop.
+//
+// Replaces what TensorFlow's double backprop evaluates for
+//   opt.compute_gradients(self.mse_, self.theta_)        multi-label-cls/icnn-back.py:120-139
+//                                                        completion/icnn.back.py:133-156
+// on the graph that unrolls nIter steps  v' = m v - lr dE/dy(y),  y' = y - m v + (1+m) v'.
+//
+// The ReLU / leaky-ReLU energy is piecewise linear in y, so the Hessian term vanishes and the
+// adjoint of every gradient evaluation g_i is kappa_i * a with a = dl/dy_N and
+//   c_N = 1+m, c_i = m c_{i+1} + 1, kappa_i = -lr c_{i+1}.
+// dl/dtheta = sum_i kappa_i d/dtheta <g_i, a>; with iterate i's activation pattern fixed, <g_i, a> is
+// the output of the linear tangent network  zt_l = act'(pre_l) o ((zt_{l-1} o cz_l) Wz_l + (a o cy_l) Wy_l)
+// whose backprop multipliers are the primal delta_l (derivation and torch-autograd pin:
+// oracle/gd_grad_np.py, tests/test_oracle_gd_grad.py).  Per layer l:
+//   dWy_l = (a o cy_l)^T Delta_l,  dcy_l = a o (Delta_l Wy_l^T),   Delta_l = sum_i kappa_i delta_l^(i)
+//   dWz_l = sum_i kappa_i (zt_{l-1}^(i) o cz_l)^T delta_l^(i)
+//   dcz_l = sum_i kappa_i zt_{l-1}^(i) o (delta_l^(i) Wz_l^T)
+//
+// Pass 1 runs the GD loop to y_N (FP32 FFMA K1, deterministic), a = loss_scale (y_N - trueY);
+// pass 2 replays the same loop (bit-identical iterates) with, per iteration: primal forward, tangent
+// forward (gated GEMM, MODE 2), backward with the dcz / Delta accumulation fused into its epilogue,
+// and one weight-gradient GEMM per Wz_l (reduction over the batch, split over a thread-block cluster
+// and reduced through distributed shared memory -- no atomics, deterministic).
+#include "gated_gemm.cuh"
+
+#include <vector>
+
+namespace icnn {
+
+size_t picnn_simt_ws_floats(const icnn_picnn* h, int B, size_t* zoff, size_t* doff);
+void out_layer_launch(const icnn_picnn* h, const icnn_gates* gt, const float* Zlast, const float* y32, float* f,
+                      float* delta, float* delta_hi, float* delta_lo, float* g, long long g_row_stride,
+                      const int* perm, const int* count, int KS, const int* skip, cudaStream_t st);
+
+struct WgradArgs {
+  int M, N, Kb;                       // C is [M, N]; reduction over Kb batch rows
+  const float* A; const float* G; int lda;   // A (optionally gated by G) [Kb, lda]
+  const float* D; int ldd;            // D [Kb, ldd]; nullptr = a column of ones (N == 1)
+  float* C; int ldc; float kappa;     // C += kappa * (A o G)^T D
+};
+
+// C[m, n] += kappa * sum_b A[b, m] G[b, m] D[b, n].  64x64 tile, 16 batch rows per stage; both
+// operands are read along their contiguous dimension.  gridDim.z = S CTAs of one cluster split the
+// batch and reduce their partial tiles through DSMEM (same scheme as gated_gemm_kernel).
+__global__ void __launch_bounds__(256) wgrad_gemm_kernel(WgradArgs a) {
+  __shared__ __align__(16) float smem_f[2 * BK * (BM + PAD) + 2 * BK * (BN + PAD)];
+  float (*As)[BK][BM + PAD] = reinterpret_cast<float (*)[BK][BM + PAD]>(smem_f);
+  float (*Bs)[BK][BN + PAD] = reinterpret_cast<float (*)[BK][BN + PAD]>(smem_f + 2 * BK * (BM + PAD));
+  const int t = threadIdx.x;
+  const int S = gridDim.z;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int ty = t / 16, tx = t % 16;
+  const int l_k = t / 16, l_c = (t % 16) * 4;
+
+  float ra[4], rb[4];
+  auto load_tiles = [&](int b0) {
+    const int b = b0 + l_k;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + l_c + i, nn = n0 + l_c + i;
+      float va = 0.f, vb = 0.f;
+      if (b < a.Kb) {
+        if (m < a.M) {
+          va = a.A[(long long)b * a.lda + m];
+          if (a.G) va *= a.G[(long long)b * a.lda + m];
+        }
+        if (nn < a.N) vb = a.D ? a.D[(long long)b * a.ldd + nn] : 1.f;
+      }
+      ra[i] = va; rb[i] = vb;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { As[buf][l_k][l_c + i] = ra[i]; Bs[buf][l_k][l_c + i] = rb[i]; }
+  };
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int nk_all = (a.Kb + BK - 1) / BK;
+  const int kt0 = (int)(((long long)nk_all * blockIdx.z) / S);
+  const int nk = (int)(((long long)nk_all * (blockIdx.z + 1)) / S) - kt0;
+  if (nk > 0) { load_tiles(kt0 * BK); store_tiles(0); }
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt0 + kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w};
+      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) store_tiles(buf ^ 1);
+    __syncthreads();
+  }
+
+  if (S == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      if (m >= a.M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int nn = n0 + tx * 4 + j;
+        if (nn < a.N) {
+          float* c = a.C + (long long)m * a.ldc + nn;
+          *c = fmaf(a.kappa, acc[i][j], *c);
+        }
+      }
+    }
+    return;
+  }
+  cg::cluster_group cluster = cg::this_cluster();
+  float (*Ps)[BN + 1] = reinterpret_cast<float (*)[BN + 1]>(smem_f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Ps[ty * 4 + i][tx * 4 + j] = acc[i][j];
+  cluster.sync();
+  const int rank = (int)cluster.block_rank();
+  const int r_lo = (BM * rank) / S, r_hi = (BM * (rank + 1)) / S;
+  for (int idx = t; idx < (r_hi - r_lo) * BN; idx += 256) {
+    const int rr = r_lo + idx / BN, cc = idx % BN;
+    float v = 0.f;
+    for (int q = 0; q < S; ++q) v += *cluster.map_shared_rank(&Ps[rr][cc], q);
+    const int m = m0 + rr, nn = n0 + cc;
+    if (m < a.M && nn < a.N) {
+      float* c = a.C + (long long)m * a.ldc + nn;
+      *c = fmaf(a.kappa, v, *c);
+    }
+  }
+  cluster.sync();
+}
+
+static cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t st) {
+  const int gx = cdiv(a.N, BN), gy = cdiv(a.M, BM);
+  const int nk = cdiv(a.Kb, BK);
+  int S = 1;
+  while (S < 8 && gx * gy * S < 296 && nk / (S * 2) >= 4) S *= 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, gy, S);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute lattr[1];
+  lattr[0].id = cudaLaunchAttributeClusterDimension;
+  lattr[0].val.clusterDim.x = 1; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = S;
+  cfg.attrs = lattr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, wgrad_gemm_kernel, a);
+}
+
+// dst += kappa * src
+__global__ void axpy_kernel(float* dst, const float* src, float kappa, long long N) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < N) dst[i] = fmaf(kappa, src[i], dst[i]);
+}
+// dst[b, j] += kappa * src[b, j] * w[j]
+__global__ void rowbcast_fma_kernel(float* dst, const float* src, const float* w, float kappa, long long N, int width) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < N) dst[i] = fmaf(kappa * src[i], w[i % width], dst[i]);
+}
+// a = scale * (y - trueY)      (d/dy_N of scale/2 * sum (y_N - trueY)^2)
+__global__ void mse_grad_kernel(float* a, const float* y, const float* trueY, float scale, long long N) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < N) a[i] = scale * (y[i] - trueY[i]);
+}
+
+struct GdbLayout {
+  size_t Z[ICNN_MAX_LAYERS], Zt[ICNN_MAX_LAYERS], Dacc[ICNN_MAX_LAYERS], dl[2], y, v, g, a, f, total;
+};
+
+static GdbLayout gdb_layout(const icnn_picnn* h, int B) {
+  GdbLayout lo{};
+  size_t off = 0;
+  auto take = [&](size_t nfl) { size_t o = off; off += (nfl + 63) & ~(size_t)63; return o; };
+  int smax = 0;
+  for (int i = 0; i < h->L; ++i) smax = h->hidden[i] > smax ? h->hidden[i] : smax;
+  for (int i = 0; i < h->L; ++i) {
+    lo.Z[i] = take((size_t)B * h->hidden[i]);
+    lo.Zt[i] = take((size_t)B * h->hidden[i]);
+    lo.Dacc[i] = take((size_t)B * h->hidden[i]);
+  }
+  lo.dl[0] = take((size_t)B * smax); lo.dl[1] = take((size_t)B * smax);
+  lo.y = take((size_t)B * h->n); lo.v = take((size_t)B * h->n); lo.g = take((size_t)B * h->n);
+  lo.a = take((size_t)B * h->n); lo.f = take((size_t)B);
+  lo.total = off;
+  return lo;
+}
+
+#define GDB_LAUNCH(expr, what)                                                                   \
+  do {                                                                                           \
+    cudaError_t _le = (expr);                                                                    \
+    if (_le != cudaSuccess) { set_error("%s launch: %s", what, cudaGetErrorString(_le)); return ICNN_E_CUDA; } \
+  } while (0)
+
+// One GD iteration's primal forward + backward on the FFMA path.  With acc != nullptr also the
+// tangent forward and the gradient accumulations (pass 2).
+struct GdbAcc { const icnn_gd_grads* gr; float kappa; };
+
+static int gdb_iteration(const icnn_picnn* h, const icnn_gates* gt, float* ws, const GdbLayout& lo,
+                         const GdbAcc* acc, cudaStream_t st) {
+  const int B = gt->B, n = h->n, L = h->L;
+  float* y = ws + lo.y; float* g = ws + lo.g; float* f = ws + lo.f; float* av = ws + lo.a;
+  float* dl[2] = {ws + lo.dl[0], ws + lo.dl[1]};
+  for (int i = 0; i < L; ++i) {
+    GemmArgs a{};
+    a.M = B; a.N = h->hidden[i]; a.K0 = h->prev(i); a.K1 = n;
+    a.A0 = i ? ws + lo.Z[i - 1] : nullptr; a.G0 = i ? gt->cz[i] : nullptr; a.lda0 = a.K0;
+    a.A1 = y; a.G1 = gt->cy[i]; a.lda1 = n; a.a1_scale = 1.f; a.a1_shift = 0.f;
+    a.W = h->Wcat[i]; a.ldw = a.N; a.D = gt->d[i]; a.Z = ws + lo.Z[i]; a.alpha = h->alpha;
+    GDB_LAUNCH(launch_gemm<0>(a, st), "gd_backward forward");
+    if (acc) {   // tangent layer: same product on (zt_{i-1}, a), pattern of Z_i, no bias
+      a.A0 = i ? ws + lo.Zt[i - 1] : nullptr; a.A1 = av; a.D = nullptr;
+      a.Zmask = ws + lo.Z[i]; a.Z = ws + lo.Zt[i];
+      GDB_LAUNCH(launch_gemm<2>(a, st), "gd_backward tangent");
+    }
+  }
+  out_layer_launch(h, gt, ws + lo.Z[L - 1], y, f, dl[0], nullptr, nullptr, g, n, nullptr, nullptr, 0, nullptr, st);
+  const int sl = h->hidden[L - 1];
+  const long long NL = (long long)B * sl;
+  if (acc) {
+    const float kp = acc->kappa;
+    axpy_kernel<<<(unsigned)((NL + 255) / 256), 256, 0, st>>>(ws + lo.Dacc[L - 1], dl[0], kp, NL);
+    rowbcast_fma_kernel<<<(unsigned)((NL + 255) / 256), 256, 0, st>>>(acc->gr->dcz[L], ws + lo.Zt[L - 1],
+                                                                      h->Wcat[L], kp, NL, sl);
+    WgradArgs w{};   // dWz_L [s_{L-1}, 1] += kappa * sum_b zt_{L-1} o cz_L   (delta_L = 1)
+    w.M = sl; w.N = 1; w.Kb = B; w.A = ws + lo.Zt[L - 1]; w.G = gt->cz[L]; w.lda = sl; w.D = nullptr; w.ldd = 1;
+    w.C = acc->gr->dWz[L]; w.ldc = 1; w.kappa = kp;
+    GDB_LAUNCH(launch_wgrad(w, st), "gd_backward wgrad(L)");
+  }
+  int cur = 0;
+  for (int i = L - 1; i >= 0; --i) {
+    if (acc && i > 0) {   // dWz_i += kappa (zt_{i-1} o cz_i)^T delta_i
+      WgradArgs w{};
+      w.M = h->prev(i); w.N = h->hidden[i]; w.Kb = B; w.A = ws + lo.Zt[i - 1]; w.G = gt->cz[i]; w.lda = w.M;
+      w.D = dl[cur]; w.ldd = w.N; w.C = acc->gr->dWz[i]; w.ldc = w.N; w.kappa = acc->kappa;
+      GDB_LAUNCH(launch_wgrad(w, st), "gd_backward wgrad");
+    }
+    GemmArgs a{};
+    a.M = B; a.N0 = h->prev(i); a.N = a.N0 + n; a.K0 = h->hidden[i]; a.K1 = 0;
+    a.A0 = dl[cur]; a.lda0 = a.K0; a.W = h->Wcat[i]; a.ldw = a.K0; a.alpha = h->alpha;
+    a.Zprev = i ? ws + lo.Z[i - 1] : nullptr; a.Cz = i ? gt->cz[i] : nullptr; a.dprev = dl[cur ^ 1];
+    a.Cy = gt->cy[i]; a.g = g; a.g_row_stride = n; a.n = n; a.g_scale = 1.f;
+    if (acc && i > 0) {
+      a.dCz = acc->gr->dcz[i]; a.Ztprev = ws + lo.Zt[i - 1]; a.Dacc = ws + lo.Dacc[i - 1]; a.kappa = acc->kappa;
+    }
+    GDB_LAUNCH(launch_gemm<1>(a, st), "gd_backward backward");
+    cur ^= 1;
+  }
+  return ICNN_OK;
+}
+
+}  // namespace icnn
+
+using namespace icnn;
+
+extern "C" size_t icnn_gd_backward_workspace_bytes(const icnn_picnn_t* h, int32_t B) {
+  if (!h || B <= 0) return 0;
+  return sizeof(float) * gdb_layout(h, B).total;
+}
+
+extern "C" int icnn_gd_backward(const icnn_picnn_t* h, const icnn_gates* gates, const float* y0,
+                                const float* trueY, float loss_scale, int32_t nIter, float lr, float momentum,
+                                float* yN, const icnn_gd_grads* gr, void* workspace, void* stream) {
+  ICNN_REQUIRE(h && gates && y0 && trueY && yN && gr && workspace, "null pointer");
+  ICNN_REQUIRE(gates->B > 0 && nIter >= 0, "empty batch or nIter < 0");
+  if (gates->in_scale != 1.f || gates->in_shift != 0.f || gates->g_scale != 1.f) {
+    set_error("icnn_gd_backward: the affine (RL) input wrapper is not on this path");
+    return ICNN_E_UNSUPPORTED;
+  }
+  const int B = gates->B, n = h->n, L = h->L;
+  for (int l = 0; l <= L; ++l)
+    ICNN_REQUIRE(gr->dWy[l] && gr->dcy[l] && (l == 0 || (gr->dWz[l] && gr->dcz[l])), "null gradient buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const GdbLayout lo = gdb_layout(h, B);
+  float* ws = static_cast<float*>(workspace);
+  const long long N = (long long)B * n;
+  const unsigned gN = (unsigned)((N + 255) / 256);
+
+  // adjoint weights of the nIter gradient evaluations
+  std::vector<double> c(nIter + 2, 0.0);
+  std::vector<float> kappa(nIter > 0 ? nIter : 1, 0.f);
+  double ksum = 0.0;
+  if (nIter > 0) {
+    c[nIter] = 1.0 + (double)momentum;
+    for (int i = nIter - 1; i >= 1; --i) c[i] = (double)momentum * c[i + 1] + 1.0;
+    for (int i = 0; i < nIter; ++i) { kappa[i] = (float)(-(double)lr * c[i + 1]); ksum += (double)kappa[i]; }
+  }
+
+  // outputs and accumulators start from zero
+  for (int l = 0; l <= L; ++l) {
+    const size_t sl = (size_t)h->width(l), sp = (size_t)h->prev(l);
+    ICNN_CUDA_CHECK(cudaMemsetAsync(gr->dWy[l], 0, sizeof(float) * n * sl, st));
+    ICNN_CUDA_CHECK(cudaMemsetAsync(gr->dcy[l], 0, sizeof(float) * N, st));
+    if (l > 0) {
+      ICNN_CUDA_CHECK(cudaMemsetAsync(gr->dWz[l], 0, sizeof(float) * sp * sl, st));
+      ICNN_CUDA_CHECK(cudaMemsetAsync(gr->dcz[l], 0, sizeof(float) * (size_t)B * sp, st));
+    }
+    if (l < L) ICNN_CUDA_CHECK(cudaMemsetAsync(ws + lo.Dacc[l], 0, sizeof(float) * (size_t)B * sl, st));
+  }
+
+  for (int pass = 0; pass < 2; ++pass) {
+    ICNN_CUDA_CHECK(cudaMemcpyAsync(ws + lo.y, y0, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+    ICNN_CUDA_CHECK(cudaMemsetAsync(ws + lo.v, 0, sizeof(float) * N, st));
+    for (int it = 0; it < nIter; ++it) {
+      GdbAcc acc{gr, kappa[it]};
+      int rc = gdb_iteration(h, gates, ws, lo, pass ? &acc : nullptr, st);
+      if (rc) return rc;
+      gd_update_kernel<<<gN, 256, 0, st>>>(ws + lo.y, ws + lo.v, ws + lo.g, N, lr, momentum);
+    }
+    if (pass == 0) {
+      ICNN_CUDA_CHECK(cudaMemcpyAsync(yN, ws + lo.y, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+      mse_grad_kernel<<<gN, 256, 0, st>>>(ws + lo.a, ws + lo.y, trueY, loss_scale, N);
+    }
+  }
+
+  // y-gate terms from the accumulated Delta_l
+  const float* av = ws + lo.a;
+  for (int l = 0; l < L && nIter > 0; ++l) {
+    WgradArgs w{};
+    w.M = n; w.N = h->hidden[l]; w.Kb = B; w.A = av; w.G = gates->cy[l]; w.lda = n;
+    w.D = ws + lo.Dacc[l]; w.ldd = w.N; w.C = gr->dWy[l]; w.ldc = w.N; w.kappa = 1.f;
+    GDB_LAUNCH(launch_wgrad(w, st), "gd_backward wgrad(Wy)");
+    GemmArgs a{};   // dcy_l = a o (Delta_l Wy_l^T): the backward GEMM against the Wy rows of Wcat_l
+    a.M = B; a.N0 = 0; a.N = n; a.K0 = h->hidden[l]; a.K1 = 0; a.A0 = ws + lo.Dacc[l]; a.lda0 = a.K0;
+    a.W = h->Wcat[l] + (size_t)h->prev(l) * h->hidden[l]; a.ldw = a.K0; a.alpha = h->alpha;
+    a.Cy = av; a.g = gr->dcy[l]; a.g_row_stride = n; a.n = n; a.g_scale = 1.f;
+    GDB_LAUNCH(launch_gemm<1>(a, st), "gd_backward dcy");
+  }
+  if (nIter > 0) {   // output layer: Delta_L = sum_i kappa_i for every sample
+    WgradArgs w{};
+    w.M = n; w.N = 1; w.Kb = B; w.A = av; w.G = gates->cy[L]; w.lda = n; w.D = nullptr; w.ldd = 1;
+    w.C = gr->dWy[L]; w.ldc = 1; w.kappa = (float)ksum;
+    GDB_LAUNCH(launch_wgrad(w, st), "gd_backward wgrad(Wy_L)");
+    rowbcast_fma_kernel<<<gN, 256, 0, st>>>(gr->dcy[L], av, h->Wcat[L] + h->hidden[L - 1], (float)ksum, N, n);
+  }
+  ICNN_CUDA_CHECK(cudaGetLastError());
+  return ICNN_OK;
+}

@@ -177,6 +177,27 @@ int icnn_gd_solve(const icnn_picnn_t* h, const icnn_gates* gates, float* y32, fl
                   float* f_out, int32_t nIter, float lr, float momentum, void* workspace,
                   void* stream);
 
+/* ---- training backward of the unrolled GD loop ------------------------ */
+/* replaces: TensorFlow's double backprop behind opt.compute_gradients(self.mse_, self.theta_) on the
+ * graph that unrolls the momentum-GD loop (multi-label-cls/icnn-back.py:120-139,
+ * completion/icnn.back.py:133-156).  Runs the loop from y0 [B,n] (f32), writes y_N to yN [B,n], takes
+ * a = loss_scale * (y_N - trueY) as d loss / d y_N (mse_ = reduce_mean(square(yn - trueY)):
+ * loss_scale = 2/(B n); completion: 2*255^2/(B n)) and returns d loss / d (y-path weights and gates):
+ *   dWy[l] [n, s_l], dWz[l] [s_{l-1}, s_l], dcy[l] [B, n], dcz[l] [B, s_{l-1}]   (l = 0..L; [0] of
+ *   dWz/dcz unused; the additive gate d_l gets no gradient).  All buffers device f32, overwritten.
+ * The x-path parameters follow from (dcy, dcz) by ordinary dense-layer backprop on the caller's side.
+ * FP32 FFMA path; the affine RL wrapper is not supported here (ICNN_E_UNSUPPORTED). */
+typedef struct {
+  float* const* dWy;
+  float* const* dWz;
+  float* const* dcy;
+  float* const* dcz;
+} icnn_gd_grads;
+size_t icnn_gd_backward_workspace_bytes(const icnn_picnn_t* h, int32_t B);
+int icnn_gd_backward(const icnn_picnn_t* h, const icnn_gates* gates, const float* y0, const float* trueY,
+                     float loss_scale, int32_t nIter, float lr, float momentum, float* yN,
+                     const icnn_gd_grads* grads, void* workspace, void* stream);
+
 /* ---- RL Adam argmin -------------------------------------------------- */
 /* replaces: Agent.adam (RL/src/icnn.py:160-215) applied to [negQ - entropy(act), d/dact]
  * (RL/src/icnn.py:60-63,127-131,455-458): batched Adam on the actions with best-so-far tracking and

@@ -1,0 +1,129 @@
+"""d mse / d theta through the unrolled momentum-GD loop (multi-label-cls/icnn-back.py:116-139) on the
+GPU vs the torch-autograd golden vectors and the float64 numpy restatement.
+
+Tolerance: the device path is float32 (FFMA GEMMs, float32 accumulation over the batch and the
+nIter iterations); every gradient array must agree with the float64 reference to 2e-4 of that
+array's largest entry where no ReLU kink flips (measured 1e-6: profiles/r01_gd_grad.md)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gd_grad_np, picnn_np, synth
+from icnn_b200.workloads import synth_params
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 2e-4
+PTOL = 5e-3   # parameter gradients when kink flips are possible (see test_matches_oracle)
+
+
+def relerr(a, b):
+    return float(np.abs(np.asarray(a, dtype=np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def test_matches_autograd_golden(golden_dir):
+    import icnn_b200
+    from oracle.gen_golden_gd_grad import CASES, true_labels
+    gold = np.load(os.path.join(golden_dir, "gd_grad.npz"))
+    for tag, (name, B, nIter, lr, mom) in CASES.items():
+        p, x, y0 = synth.make_inputs(name, B=B)
+        tY = true_labels(B, p.n)
+        net = icnn_b200.PICNN.from_params(p)
+        yN, gr = icnn_b200.gd_grad.gd_grad(net.bind(x), y0, tY, nIter=nIter, lr=lr, momentum=mom, x=x)
+        assert np.abs(yN - gold[tag + "_yN"]).max() < 2e-5
+        worst = {}
+        for k in ("Wy", "Wz", "Wu", "bu", "Wzu", "bzu", "Wyu", "byu"):
+            for i, g in enumerate(gr[k]):
+                key = "%s_%s%d" % (tag, k, i)
+                if g is None:
+                    assert key not in gold.files
+                    continue
+                worst[key] = relerr(g, gold[key])
+        print(tag, "max rel err", max(worst.values()), max(worst, key=worst.get))
+        assert max(worst.values()) < RTOL, worst
+
+
+def _dims_case(m, n, hidden, B, seed):
+    p = synth_params(seed, m, n, hidden)
+    for i in range(len(p.Wy)):
+        p.Wy[i] = (p.Wy[i].astype(np.float32) * np.float32(3.0)).astype(np.float64)
+    rs = np.random.RandomState(seed + 1)
+    x = rs.randn(B, m).astype(np.float32).astype(np.float64)
+    y0 = np.full((B, n), 0.5)
+    tY = (rs.uniform(size=(B, n)) < 0.2).astype(np.float64)
+    return p, x, y0, tY
+
+
+@pytest.mark.parametrize("dims,B,nIter,lr,mom", [
+    ((1836, 159, [600, 159]), 512, 30, 0.01, 0.3),     # C3 dims, the multi-label script's defaults
+    ((64, 512, [1024, 1024]), 200, 6, 0.01, 0.9),      # wide layers: split-K clusters in every GEMM
+    ((12, 37, [50, 21, 33]), 77, 10, 0.02, 0.5),       # odd widths, three hidden layers, ragged tiles
+])
+def test_matches_oracle(dims, B, nIter, lr, mom):
+    import icnn_b200
+    m, n, hidden = dims
+    p, x, y0, tY = _dims_case(m, n, hidden, B, seed=21)
+    gts = picnn_np.gates(p, x)
+    yo, go = gd_grad_np.gd_backward(p, gts, y0, nIter, lr, mom, lambda y: 2.0 * (y - tY) / y.size)
+    xo = gd_grad_np.xpath_backward(p, x, go["dcy"], go["dcz"])
+    net = icnn_b200.PICNN.from_params(p)
+    yN, gr = icnn_b200.gd_grad.gd_grad(net.bind(x), y0, tY, nIter=nIter, lr=lr, momentum=mom, x=x)
+    # a float32 iterate that lands on the other side of a ReLU kink changes that sample's gradient by
+    # O(1) for one step (the long-horizon sensitivity DESIGN.md section 4 describes for the bundle
+    # path): y_N and the per-sample gate adjoints are compared row-wise, >= 99 % of the samples within
+    # tolerance; the parameter gradients (sums over the batch) absorb the few flipped rows
+    dy = np.abs(yN - yo).max(axis=1)
+    assert np.median(dy) < 2e-6 and np.mean(dy < 1e-4) >= 0.99, (np.median(dy), dy.max())
+    errs, rows = {}, {}
+
+    def rowfrac(a, b):
+        d = np.abs(np.asarray(a, dtype=np.float64) - b).max(axis=1) / max(np.abs(b).max(), 1e-30)
+        return float(np.mean(d < RTOL))
+
+    for l in range(p.L + 1):
+        errs["Wy%d" % l] = relerr(gr["Wy"][l], go["dWy"][l])
+        rows["dcy%d" % l] = rowfrac(gr["dcy"][l], go["dcy"][l])
+        errs["Wyu%d" % l] = relerr(gr["Wyu"][l], xo["dWyu"][l])
+        if l > 0:
+            errs["Wz%d" % l] = relerr(gr["Wz"][l], go["dWz"][l])
+            rows["dcz%d" % l] = rowfrac(gr["dcz"][l], go["dcz"][l])
+            errs["Wzu%d" % l] = relerr(gr["Wzu"][l], xo["dWzu"][l])
+    for l in range(p.L):
+        errs["Wu%d" % l] = relerr(gr["Wu"][l], xo["dWu"][l])
+    print(dims, "dy max %.2e" % dy.max(), "param max rel err %.2e" % max(errs.values()), max(errs, key=errs.get),
+          "min row fraction %.4f" % min(rows.values()), errs)
+    assert min(rows.values()) >= 0.99, rows
+    assert max(errs.values()) < PTOL, errs
+
+
+def test_yn_is_the_gd_solve_iterate():
+    import icnn_b200
+    p, x, y0 = synth.make_inputs("C3", B=128)
+    tY = np.zeros_like(y0)
+    fg = icnn_b200.PICNN.from_params(p).bind(x)
+    yN, _ = icnn_b200.gd_grad.gd_grad(fg, y0, tY, nIter=30)
+    ys, _ = icnn_b200.gd.solve(fg, y0, nIter=30)
+    assert np.abs(yN - ys).max() < 1e-4
+
+
+def test_zero_iterations_and_errors():
+    import icnn_b200
+    p, x, y0 = synth.make_inputs("C1", B=8)
+    net = icnn_b200.PICNN.from_params(p)
+    yN, gr = icnn_b200.gd_grad.gd_grad(net.bind(x), y0, np.zeros_like(y0), nIter=0)
+    np.testing.assert_array_equal(yN, y0.astype(np.float32))
+    assert all(not np.any(g) for g in gr["Wy"])
+    with pytest.raises(ValueError):
+        icnn_b200.gd_grad.gd_grad(net.bind(x, affine=True), y0, y0)
+    with pytest.raises(TypeError):
+        icnn_b200.gd_grad.gd_grad(lambda y: y, y0, y0)
+
+
+def test_make_cvx_and_proj():
+    import torch
+    from icnn_b200.gd_grad import make_cvx, proj
+    w = [None, torch.tensor([[-1.0, 2.0], [0.5, -4.0]])]
+    np.testing.assert_array_equal(proj([None, w[1].clone()])[1].numpy(), [[0, 2], [0.5, 0]])
+    np.testing.assert_array_equal(make_cvx([None, w[1].clone()])[1].numpy(), [[1, 2], [0.5, 4]])
+    np.testing.assert_array_equal(make_cvx([None, w[1].clone()], halve=True)[1].numpy(), [[0.5, 1], [0.25, 2]])
