@@ -32,6 +32,9 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+// leading dimension padded to 4 floats: 16-byte row pitch for TMA; the pad columns lie outside the
+// tensor map's extent (TMA zero-fills them), so they are never read and need no initialisation
+static inline int ld4(int k) { return (k + 3) & ~3; }
 
 }  // namespace icnn
 

@@ -26,7 +26,7 @@ struct OutArgs {
   const float* w;                        // [S + n]  = [wz_L ; wy_L]
   float in_scale, in_shift, g_scale, alpha;
   float* f; float* delta;                // [M], [M, S]
-  float* delta_hi; float* delta_lo;      // optional TF32 hi/lo split of delta (tensor-core path)
+  float* delta_hi; float* delta_lo; int delta_ld;   // optional TF32 hi/lo split of delta (tensor-core path, row pitch ld4(S))
   float* g; long long g_row_stride; const int* perm; const int* count; int KS;
   const int* skip_if_zero;
 };
@@ -52,8 +52,9 @@ __global__ void __launch_bounds__(256) out_layer_kernel(OutArgs a) {
       if (a.delta_hi) {
         // TF32 hi/lo with round-to-nearest on both parts (see tf32_rn in picnn_tc.cu)
         const float h = __uint_as_float((__float_as_uint(dl) + 0x00001000u) & 0xFFFFE000u);
-        a.delta_hi[idx] = h;
-        a.delta_lo[idx] = __uint_as_float((__float_as_uint(dl - h) + 0x00001000u) & 0xFFFFE000u);
+        const long long o = (long long)m * a.delta_ld + j;
+        a.delta_hi[o] = h;
+        a.delta_lo[o] = __uint_as_float((__float_as_uint(dl - h) + 0x00001000u) & 0xFFFFE000u);
       }
     }
     float* grow;
@@ -111,7 +112,7 @@ void out_layer_launch(const icnn_picnn* h, const icnn_gates* gt, const float* Zl
   OutArgs o{};
   o.M = B; o.S = h->hidden[L - 1]; o.n = h->n; o.Z = Zlast; o.Cz = gt->cz[L]; o.y = y32; o.Cy = gt->cy[L];
   o.D = gt->d[L]; o.w = h->Wcat[L]; o.in_scale = gt->in_scale; o.in_shift = gt->in_shift;
-  o.g_scale = gt->g_scale; o.alpha = h->alpha; o.f = f; o.delta = delta; o.delta_hi = delta_hi; o.delta_lo = delta_lo;
+  o.g_scale = gt->g_scale; o.alpha = h->alpha; o.f = f; o.delta = delta; o.delta_hi = delta_hi; o.delta_lo = delta_lo; o.delta_ld = ld4(o.S);
   o.g = g; o.g_row_stride = g_row_stride; o.perm = perm; o.count = count; o.KS = KS; o.skip_if_zero = skip;
   if (B <= 2048) out_layer_kernel<256><<<B, 256, 0, st>>>(o);          // few samples: a CTA each
   else out_layer_kernel<32><<<cdiv(B * 32, 256), 256, 0, st>>>(o);
@@ -166,8 +167,8 @@ int picnn_fg_simt(const icnn_picnn* h, const icnn_gates* gt, const float* y32, f
   return ICNN_OK;
 }
 
-// K1 dispatch: tcgen05 path for TMA-compatible shapes (every width % 4 == 0) with enough rows to
-// fill a 128-row tile, FP32 FFMA path otherwise.  ICNN_K1=simt|tc forces one.
+// K1 dispatch: tcgen05 path once there are enough rows to fill a 128-row tile, FP32 FFMA path
+// otherwise.  ICNN_K1=simt at handle creation keeps everything on the FFMA path.
 int picnn_fg_dispatch(const icnn_picnn* h, const icnn_gates* gt, const float* y32, float* f, float* g,
                       long long g_row_stride, const int* perm, const int* count, int KS, void* workspace,
                       const int* skip, cudaStream_t st) {
@@ -213,7 +214,7 @@ extern "C" int icnn_picnn_create(const icnn_picnn_desc* d, icnn_picnn_t** out, v
       if (rc) { icnn_picnn_destroy(h); return rc; }
       h->use_tc = true;
     } else if (k1 && k1[0] == 't') {
-      icnn_picnn_destroy(h); set_error("ICNN_K1=tc but the shape is not TMA-compatible (widths %% 4)"); return ICNN_E_UNSUPPORTED;
+      icnn_picnn_destroy(h); set_error("ICNN_K1=tc but cuTensorMapEncodeTiled is unavailable"); return ICNN_E_UNSUPPORTED;
     }
   }
   cudaError_t e = cudaStreamSynchronize(st);

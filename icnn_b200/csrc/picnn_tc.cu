@@ -141,8 +141,8 @@ struct TcArgs {
   // forward epilogue: Z = act(acc + D); optional next-layer operand A'_{next}[:, 0:N] = Z o Cz_next (hi/lo)
   const float* D; float* Z; float alpha;
   const float* Cz_next; float* nxt_hi; float* nxt_lo; int nxt_ld;
-  // backward epilogue: columns < N0 -> delta_prev = act'(Zprev) o Cz o acc (hi/lo, ld N0); else g += ...
-  int N0; const float* Zprev; const float* Cz; float* dprev_hi; float* dprev_lo;
+  // backward epilogue: columns < N0 -> delta_prev = act'(Zprev) o Cz o acc (hi/lo, row pitch dprev_ld); else g += ...
+  int N0; const float* Zprev; const float* Cz; float* dprev_hi; float* dprev_lo; int dprev_ld;
   const float* Cy; float* g; long long g_row_stride; const int* perm; const int* count; int KS; int n;
   float g_scale;
   float* C;  // mode 2
@@ -318,8 +318,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               const float da = __ldg(a.Zprev + idx) > 0.f ? 1.f : a.alpha;
               const float p = da * __ldg(a.Cz + idx) * acc;
               const float h = tf32_hi(p);
-              a.dprev_hi[idx] = h;
-              a.dprev_lo[idx] = tf32_lo(p, h);
+              a.dprev_hi[(long long)m * a.dprev_ld + nn] = h;
+              a.dprev_lo[(long long)m * a.dprev_ld + nn] = tf32_lo(p, h);
             } else {
               const int e = nn - a.N0;
               grow[e] = fmaf(a.g_scale * __ldg(a.Cy + (long long)m * a.n + e), acc, grow[e]);
@@ -400,12 +400,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             }
           } else if (a.mode == 1) {
             if (nn < a.N0) {
-              const long long idx = (long long)m * a.N0 + nn;
               const float da = in0[i] > 0.f ? 1.f : a.alpha;
               const float p = da * in1[i] * acc[i];
               const float h = tf32_hi(p);
-              a.dprev_hi[idx] = h;
-              a.dprev_lo[idx] = tf32_lo(p, h);
+              a.dprev_hi[(long long)m * a.dprev_ld + nn] = h;
+              a.dprev_lo[(long long)m * a.dprev_ld + nn] = tf32_lo(p, h);
             } else {
               const int e = nn - a.N0;
               reinterpret_cast<float*>(gp[i])[e] = fmaf(a.g_scale * in0[i], acc[i], in1[i]);
@@ -466,15 +465,17 @@ __global__ void gate_y_kernel(GateYArgs a) {
   }
 }
 
-__global__ void split_tf32_kernel(const float* src, float* hi, float* lo, long long N) {
+// src [R, C] dense -> hi/lo [R, C] with row pitch ld
+__global__ void split_tf32_kernel(const float* src, float* hi, float* lo, long long R, int C, int ld) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= N) return;
+  if (i >= R * C) return;
+  const long long o = (i / C) * ld + (i % C);
   const float x = src[i], h = tf32_hi(x);
-  hi[i] = h;
-  lo[i] = tf32_lo(x, h);
+  hi[o] = h;
+  lo[o] = tf32_lo(x, h);
 }
-// dst[c, r] = src[r, c] split hi/lo   (src [R, C] row-major -> dst [C, R])
-__global__ void transpose_split_kernel(const float* src, float* hi, float* lo, int R, int C) {
+// dst[c, r] = src[r, c] split hi/lo   (src [R, C] row-major -> dst [C, R] with row pitch ldr)
+__global__ void transpose_split_kernel(const float* src, float* hi, float* lo, int R, int C, int ldr) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -486,8 +487,8 @@ __global__ void transpose_split_kernel(const float* src, float* hi, float* lo, i
     const int c = c0 + i, r = r0 + threadIdx.x;
     if (c < C && r < R) {
       const float x = tile[threadIdx.x][i], h = tf32_hi(x);
-      hi[(long long)c * R + r] = h;
-      lo[(long long)c * R + r] = tf32_lo(x, h);
+      hi[(long long)c * ldr + r] = h;
+      lo[(long long)c * ldr + r] = tf32_lo(x, h);
     }
   }
 }
@@ -583,26 +584,28 @@ static int launch_tc_gemm(const float* Ah, const float* Al, long long lda, const
   return ICNN_OK;
 }
 
-// shapes the tensor-core path accepts: every contraction / leading dimension a multiple of 4
-// floats (16-byte TMA strides)
+// Every shape is accepted: TMA needs 16-byte row pitches, so every library-owned operand (packed
+// weights, K-concatenated activations, delta) is laid out with its leading dimension padded to 4
+// floats (ld4); the tensor maps keep the true extents, so the pad is never read.
 bool picnn_tc_supported(const icnn_picnn* h) {
-  if (h->n % 4) return false;
-  for (int i = 0; i < h->L; ++i) if (h->hidden[i] % 4) return false;
+  (void)h;
   return get_encode() != nullptr;
 }
 
 int picnn_tc_prepare_weights(icnn_picnn* h, cudaStream_t st) {
   for (int i = 0; i < h->L; ++i) {  // hidden layers only; the width-1 output layer stays on the SIMT kernel
     const int si = h->hidden[i], kf = h->prev(i) + h->n;
-    const size_t bytes = sizeof(float) * (size_t)kf * si;
+    // Wb: [kf, si] pitch ld4(si) (backward B operand); Wf: [si, kf] pitch ld4(kf) (forward B operand)
     for (float** p : {&h->Wb_hi[i], &h->Wb_lo[i], &h->Wf_hi[i], &h->Wf_lo[i]}) {
+      const bool wb = (p == &h->Wb_hi[i] || p == &h->Wb_lo[i]);
+      const size_t bytes = sizeof(float) * (wb ? (size_t)kf * ld4(si) : (size_t)si * ld4(kf));
       cudaError_t e = cudaMalloc(p, bytes);
       if (e != cudaSuccess) { set_error("cudaMalloc tc weights: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
     }
     const long long N = (long long)kf * si;
-    split_tf32_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(h->Wcat[i], h->Wb_hi[i], h->Wb_lo[i], N);
+    split_tf32_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(h->Wcat[i], h->Wb_hi[i], h->Wb_lo[i], kf, si, ld4(si));
     dim3 tb(32, 8), tg(cdiv(si, 32), cdiv(kf, 32));
-    transpose_split_kernel<<<tg, tb, 0, st>>>(h->Wcat[i], h->Wf_hi[i], h->Wf_lo[i], kf, si);
+    transpose_split_kernel<<<tg, tb, 0, st>>>(h->Wcat[i], h->Wf_hi[i], h->Wf_lo[i], kf, si, ld4(kf));
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("tc weight prep: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
@@ -615,18 +618,19 @@ void picnn_tc_free_weights(icnn_picnn* h) {
       if (*p) { cudaFree(*p); *p = nullptr; }
 }
 
-// extra workspace (floats) after the SIMT part: per hidden layer A'_i hi/lo [B, s_{i-1}+n]; delta hi/lo x2
+// extra workspace (floats) after the SIMT part: per hidden layer A'_i hi/lo [B, s_{i-1}+n] (pitch ld4);
+// delta hi/lo x2 (pitch ld4)
 size_t picnn_tc_ws_floats(const icnn_picnn* h, int B, size_t* aoff, size_t* doff) {
   size_t off = 0;
   int smax = 0;
   auto al = [](size_t v) { return (v + 63) & ~(size_t)63; };
   for (int i = 0; i < h->L; ++i) {
-    const size_t sz = al((size_t)B * (h->prev(i) + h->n));
+    const size_t sz = al((size_t)B * ld4(h->prev(i) + h->n));
     if (aoff) { aoff[2 * i] = off; aoff[2 * i + 1] = off + sz; }
     off += 2 * sz;
     smax = h->hidden[i] > smax ? h->hidden[i] : smax;
   }
-  const size_t dsz = al((size_t)B * smax);
+  const size_t dsz = al((size_t)B * ld4(smax));
   if (doff) for (int j = 0; j < 4; ++j) doff[j] = off + j * dsz;
   off += 4 * dsz;
   return off;
@@ -655,7 +659,7 @@ int picnn_fg_tc(const icnn_picnn* h, const icnn_gates* gt, const float* y32, flo
   {  // (s y + t) o cy_i for every hidden layer, straight into the K-concatenated operands
     GateYArgs ga{};
     ga.B = B; ga.n = n; ga.L = L; ga.y = y32; ga.sc = gt->in_scale; ga.sh = gt->in_shift; ga.skip_if_zero = skip;
-    for (int i = 0; i < L; ++i) { ga.cy[i] = gt->cy[i]; ga.hi[i] = Ah[i]; ga.lo[i] = Al[i]; ga.ld[i] = h->prev(i) + n; ga.off[i] = h->prev(i); }
+    for (int i = 0; i < L; ++i) { ga.cy[i] = gt->cy[i]; ga.hi[i] = Ah[i]; ga.lo[i] = Al[i]; ga.ld[i] = ld4(h->prev(i) + n); ga.off[i] = h->prev(i); }
     const long long N = (long long)B * n;
     gate_y_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ga);
   }
@@ -663,8 +667,8 @@ int picnn_fg_tc(const icnn_picnn* h, const icnn_gates* gt, const float* y32, flo
     TcArgs a{};
     a.M = B; a.N = h->hidden[i]; a.K = h->prev(i) + n; a.mode = 0;
     a.D = gt->d[i]; a.Z = Z[i]; a.alpha = h->alpha; a.skip_if_zero = skip;
-    if (i + 1 < L) { a.Cz_next = gt->cz[i + 1]; a.nxt_hi = Ah[i + 1]; a.nxt_lo = Al[i + 1]; a.nxt_ld = h->hidden[i] + n; }
-    int rc = launch_tc_gemm(Ah[i], Al[i], a.K, h->Wf_hi[i], h->Wf_lo[i], a.K, a, st);
+    if (i + 1 < L) { a.Cz_next = gt->cz[i + 1]; a.nxt_hi = Ah[i + 1]; a.nxt_lo = Al[i + 1]; a.nxt_ld = ld4(h->hidden[i] + n); }
+    int rc = launch_tc_gemm(Ah[i], Al[i], ld4(a.K), h->Wf_hi[i], h->Wf_lo[i], ld4(a.K), a, st);
     if (rc) return rc;
   }
   out_layer_launch(h, gt, Z[L - 1], y32, f, nullptr, dh[0], dl[0], g, g_row_stride, perm, count, KS, skip, st);
@@ -672,10 +676,10 @@ int picnn_fg_tc(const icnn_picnn* h, const icnn_gates* gt, const float* y32, flo
   for (int i = L - 1; i >= 0; --i) {
     TcArgs a{};
     a.M = B; a.N0 = h->prev(i); a.N = a.N0 + n; a.K = h->hidden[i]; a.mode = 1; a.alpha = h->alpha;
-    a.Zprev = i ? Z[i - 1] : nullptr; a.Cz = i ? gt->cz[i] : nullptr; a.dprev_hi = dh[cur ^ 1]; a.dprev_lo = dl[cur ^ 1];
+    a.Zprev = i ? Z[i - 1] : nullptr; a.Cz = i ? gt->cz[i] : nullptr; a.dprev_hi = dh[cur ^ 1]; a.dprev_lo = dl[cur ^ 1]; a.dprev_ld = ld4(a.N0);
     a.Cy = gt->cy[i]; a.g = g; a.g_row_stride = g_row_stride; a.perm = perm; a.count = count; a.KS = KS; a.n = n;
     a.g_scale = gt->g_scale; a.skip_if_zero = skip;
-    int rc = launch_tc_gemm(dh[cur], dl[cur], a.K, h->Wb_hi[i], h->Wb_lo[i], a.K, a, st);
+    int rc = launch_tc_gemm(dh[cur], dl[cur], ld4(a.K), h->Wb_hi[i], h->Wb_lo[i], ld4(a.K), a, st);
     if (rc) return rc;
     cur ^= 1;
   }
@@ -700,13 +704,13 @@ int picnn_xpath_prepare(icnn_picnn* h, int m, const float* const* Wu, const floa
     const int Nt = wu + wzu + n + wd;
     h->xN[s] = Nt; h->xK[s] = K;
     for (float** p : {&h->Xw_hi[s], &h->Xw_lo[s]})
-      if (cudaMalloc(p, sizeof(float) * (size_t)Nt * K) != cudaSuccess) { set_error("cudaMalloc x-path weights"); return ICNN_E_CUDA; }
+      if (cudaMalloc(p, sizeof(float) * (size_t)Nt * ld4(K)) != cudaSuccess) { set_error("cudaMalloc x-path weights"); return ICNN_E_CUDA; }
     if (cudaMalloc(&h->Xbias[s], sizeof(float) * Nt) != cudaSuccess) { set_error("cudaMalloc x-path bias"); return ICNN_E_CUDA; }
     int off = 0;
     auto put = [&](const float* W, const float* bvec, int width) {   // W [K, width] row-major -> rows off.. of [Nt, K]
       if (width == 0) return;
       dim3 tb(32, 8), tg(cdiv(width, 32), cdiv(K, 32));
-      transpose_split_kernel<<<tg, tb, 0, st>>>(W, h->Xw_hi[s] + (size_t)off * K, h->Xw_lo[s] + (size_t)off * K, K, width);
+      transpose_split_kernel<<<tg, tb, 0, st>>>(W, h->Xw_hi[s] + (size_t)off * ld4(K), h->Xw_lo[s] + (size_t)off * ld4(K), K, width, ld4(K));
       cudaMemcpyAsync(h->Xbias[s] + off, bvec, sizeof(float) * width, cudaMemcpyDeviceToDevice, st);
       off += width;
     };
@@ -727,12 +731,12 @@ void picnn_xpath_free(icnn_picnn* h) {
       if (*p) { cudaFree(*p); *p = nullptr; }
 }
 
-// workspace (floats): x hi/lo [B, m], u_s hi/lo [B, s_s] for s < L
+// workspace (floats): x hi/lo [B, m], u_s hi/lo [B, s_s] for s < L (row pitch ld4)
 size_t picnn_xpath_ws_floats(const icnn_picnn* h, int B, size_t* off) {
   size_t o = 0;
   auto al = [](size_t v) { return (v + 63) & ~(size_t)63; };
   for (int s = 0; s <= h->L; ++s) {
-    const size_t sz = al((size_t)B * (s == 0 ? h->m : h->hidden[s - 1]));
+    const size_t sz = al((size_t)B * ld4(s == 0 ? h->m : h->hidden[s - 1]));
     if (off) { off[2 * s] = o; off[2 * s + 1] = o + sz; }
     o += 2 * sz;
   }
@@ -745,7 +749,7 @@ int picnn_gates_tc(const icnn_picnn* h, const float* x, int B, float* const* cz,
   size_t off[2 * (ICNN_MAX_LAYERS + 1)];
   picnn_xpath_ws_floats(h, B, off);
   float* ws = static_cast<float*>(workspace);
-  split_tf32_kernel<<<(unsigned)(((long long)B * h->m + 255) / 256), 256, 0, st>>>(x, ws + off[0], ws + off[1], (long long)B * h->m);
+  split_tf32_kernel<<<(unsigned)(((long long)B * h->m + 255) / 256), 256, 0, st>>>(x, ws + off[0], ws + off[1], B, h->m, ld4(h->m));
   for (int s = 0; s <= L; ++s) {
     const int wu = s < L ? h->hidden[s] : 0, wzu = s >= 1 ? h->hidden[s - 1] : 0, wd = h->width(s);
     TcArgs a{};
@@ -753,14 +757,14 @@ int picnn_gates_tc(const icnn_picnn* h, const float* x, int B, float* const* cz,
     int r = 0, c = 0;
     a.rbeg[0] = 0;
     if (s < L) {   // u_s = (relu for s < L-1)(P Wu + bu): only needed as the next GEMM's hi/lo operand
-      a.rrelu[r] = (s < L - 1); a.rdst[r] = nullptr; a.rld[r] = wu; a.r0_hi = ws + off[2 * (s + 1)]; a.r0_lo = ws + off[2 * (s + 1) + 1];
+      a.rrelu[r] = (s < L - 1); a.rdst[r] = nullptr; a.rld[r] = ld4(wu); a.r0_hi = ws + off[2 * (s + 1)]; a.r0_lo = ws + off[2 * (s + 1) + 1];
       c += wu; a.rbeg[++r] = c;
     }
     if (s >= 1) { a.rrelu[r] = 1; a.rdst[r] = cz[s]; a.rld[r] = wzu; c += wzu; a.rbeg[++r] = c; }
     a.rrelu[r] = 0; a.rdst[r] = cy[s]; a.rld[r] = n; c += n; a.rbeg[++r] = c;
     a.rrelu[r] = 0; a.rdst[r] = d[s]; a.rld[r] = wd; c += wd; a.rbeg[++r] = c;
     a.nr = r;
-    int rc = launch_tc_gemm(ws + off[2 * s], ws + off[2 * s + 1], a.K, h->Xw_hi[s], h->Xw_lo[s], a.K, a, st);
+    int rc = launch_tc_gemm(ws + off[2 * s], ws + off[2 * s + 1], ld4(a.K), h->Xw_hi[s], h->Xw_lo[s], ld4(a.K), a, st);
     if (rc) return rc;
   }
   return ICNN_OK;
@@ -776,7 +780,7 @@ extern "C" int icnn_picnn_set_xpath(icnn_picnn_t* h, int32_t m, const float* con
                                     void* stream) {
   ICNN_REQUIRE(h && Wu && bu && Wzu && bzu && Wyu && byu && Wzx && bzx, "null pointer");
   ICNN_REQUIRE(m >= 1, "m must be positive");
-  if (!h->use_tc || (m % 4) != 0) { set_error("x-path kernel needs the tensor-core path and m %% 4 == 0"); return ICNN_E_UNSUPPORTED; }
+  if (!h->use_tc) { set_error("x-path kernel needs the tensor-core path (ICNN_K1=simt build of the handle)"); return ICNN_E_UNSUPPORTED; }
   if (h->has_xpath) picnn_xpath_free(h);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = picnn_xpath_prepare(h, m, Wu, bu, Wzu, bzu, Wyu, byu, Wzx, bzx, st);
@@ -799,16 +803,17 @@ extern "C" int icnn_picnn_gates(const icnn_picnn_t* h, const float* x, int32_t B
 }
 
 // Self test of the tensor-core GEMM: C[M,N] = A[M,K] * B[N,K]^T (3xTF32), all device, row-major.
-// scratch: 2*M*K + 2*N*K floats.
+// scratch: (2*M + 2*N) * ((K+3)&~3) floats.
 extern "C" int icnn_tc_gemm_selftest(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
                                      float* scratch, void* stream) {
   ICNN_REQUIRE(A && B && C && scratch, "null pointer");
-  ICNN_REQUIRE(M > 0 && N > 0 && K > 0 && K % 4 == 0, "need K % 4 == 0");
+  ICNN_REQUIRE(M > 0 && N > 0 && K > 0, "empty problem");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  float* Ah = scratch; float* Al = Ah + (size_t)M * K; float* Bh = Al + (size_t)M * K; float* Bl = Bh + (size_t)N * K;
-  split_tf32_kernel<<<(unsigned)(((long long)M * K + 255) / 256), 256, 0, st>>>(A, Ah, Al, (long long)M * K);
-  split_tf32_kernel<<<(unsigned)(((long long)N * K + 255) / 256), 256, 0, st>>>(B, Bh, Bl, (long long)N * K);
+  const int ld = ld4(K);
+  float* Ah = scratch; float* Al = Ah + (size_t)M * ld; float* Bh = Al + (size_t)M * ld; float* Bl = Bh + (size_t)N * ld;
+  split_tf32_kernel<<<(unsigned)(((long long)M * K + 255) / 256), 256, 0, st>>>(A, Ah, Al, M, K, ld);
+  split_tf32_kernel<<<(unsigned)(((long long)N * K + 255) / 256), 256, 0, st>>>(B, Bh, Bl, N, K, ld);
   TcArgs a{};
   a.M = M; a.N = N; a.K = K; a.mode = 2; a.C = C;
-  return launch_tc_gemm(Ah, Al, K, Bh, Bl, K, a, st);
+  return launch_tc_gemm(Ah, Al, ld, Bh, Bl, ld, a, st);
 }

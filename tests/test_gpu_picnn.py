@@ -18,7 +18,7 @@ def _net(name, B):
     return cfg, p, x, y0, icnn_b200.PICNN.from_params(p)
 
 
-@pytest.mark.parametrize("name,B", [("C1", 64), ("C1", 1), ("C3", 77), ("C4", 300), ("T", 130), ("C5", 5), ("C5", 70),
+@pytest.mark.parametrize("name,B", [("C1", 64), ("C1", 1), ("C3", 77), ("C3", 40), ("C4", 300), ("T", 130), ("C5", 5), ("C5", 70),
                                     ("C2", 400)])
 def test_fg_matches_oracle(name, B):
     cfg, p, x, y0, net = _net(name, B)
@@ -27,7 +27,7 @@ def test_fg_matches_oracle(name, B):
     f, g = fg(y)
     fo, go = picnn_np.make_fg(p, x, affine=cfg["affine"])(y)
     assert f.dtype == np.float32 and g.dtype == np.float32 and g.shape == y.shape
-    # FP32 FFMA path: ~3e-7.  tcgen05 3xTF32 path (>= 64 rows, widths % 4 == 0): the operand split is
+    # FP32 FFMA path: ~3e-7.  tcgen05 3xTF32 path (>= 64 rows): the operand split is
     # exact to 2^-22, but the tensor core rounds its FP32 accumulator toward zero on every MMA, a
     # systematic -5e-6 relative bias per GEMM at K = 2048 even with three rotating accumulators
     # (measured: 1e-5 on g at C2, 2e-5 on f through the 4 x 1024 layers of C5)
@@ -86,9 +86,36 @@ def test_xpath_gates_kernel_matches_oracle(name, B):
             assert np.abs(g - want).max() <= 1e-5 * max(1.0, np.abs(want).max())
 
 
-def test_xpath_falls_back_for_unaligned_widths():
-    cfg, p, x, y0, net = _net("C3", 16)      # n = 159: not TMA-compatible -> cuBLAS x-path, FFMA K1
+def test_xpath_falls_back_without_the_tensor_core_path(monkeypatch):
+    monkeypatch.setenv("ICNN_K1", "simt")    # FFMA-only handle -> cuBLAS x-path through torch.addmm
+    cfg, p, x, y0, net = _net("C3", 16)
     assert not net._xpath
     cz, cy, d = net.gates(x)
     ocz, ocy, od = picnn_np.gates(p, x)
     assert np.abs(cy[0].cpu().numpy() - ocy[0]).max() <= 1e-4 * max(1.0, np.abs(ocy[0]).max())
+
+
+@pytest.mark.parametrize("dims,B", [((13, 37, [50, 21, 33]), 200), ((17, 6, [200, 200]), 1000),
+                                    ((1836, 159, [600, 159]), 300), ((5, 3, [2]), 64)])
+def test_unaligned_widths_take_the_tensor_core_path(dims, B):
+    """Widths that are not multiples of 4 floats (C3: n = 159, C4: n = 6): the library pads the leading
+    dimension of its own operands to a 16-byte pitch, the tensor maps keep the true extents."""
+    import icnn_b200
+    from icnn_b200.workloads import synth_params
+    m, n, hidden = dims
+    p = synth_params(31, m, n, hidden)
+    rs = np.random.RandomState(32)
+    x = rs.randn(B, m).astype(np.float32).astype(np.float64)
+    y = rs.uniform(0.02, 0.98, size=(B, n)).astype(np.float32).astype(np.float64)
+    net = icnn_b200.PICNN.from_params(p)
+    assert net._xpath
+    ocz, ocy, od = picnn_np.gates(p, x)
+    cz, cy, d = net.gates(x)
+    for i in range(p.L + 1):
+        for got, want in ((cz[i], ocz[i]), (cy[i], ocy[i]), (d[i], od[i])):
+            if want is not None:
+                assert np.abs(got.cpu().numpy() - want).max() <= 1e-5 * max(1.0, np.abs(want).max())
+    f, g = net.bind(x)(y)
+    fo, go = picnn_np.make_fg(p, x)(y)
+    assert np.abs(f - fo).max() <= 1e-5 * max(1.0, np.abs(fo).max())
+    assert np.abs(g - go).max() <= 1e-5 * max(1.0, np.abs(go).max())
