@@ -36,6 +36,15 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // tensor map's extent (TMA zero-fills them), so they are never read and need no initialisation
 static inline int ld4(int k) { return (k + 3) & ~3; }
 
+// buffers of the GD training backward on the tensor-core GEMMs (layout owned by gd_backward.cu)
+struct GdbTcBufs {
+  float* y; float* g;
+  float* Z[ICNN_MAX_LAYERS]; float* Zt[ICNN_MAX_LAYERS]; float* Dacc[ICNN_MAX_LAYERS];
+  float* Ah[ICNN_MAX_LAYERS]; float* Al[ICNN_MAX_LAYERS];     // primal K-concatenated operands (TF32 hi/lo)
+  float* Ath[ICNN_MAX_LAYERS]; float* Atl[ICNN_MAX_LAYERS];   // tangent operands
+  float* dh[2]; float* dl[2]; float* dp[2];                   // delta: hi / lo / plain, ping-pong
+};
+
 }  // namespace icnn
 
 // Library-owned weight descriptor.

@@ -16,18 +16,27 @@
 //   dWz_l = sum_i kappa_i (zt_{l-1}^(i) o cz_l)^T delta_l^(i)
 //   dcz_l = sum_i kappa_i zt_{l-1}^(i) o (delta_l^(i) Wz_l^T)
 //
-// Pass 1 runs the GD loop to y_N (FP32 FFMA K1, deterministic), a = loss_scale (y_N - trueY);
-// pass 2 replays the same loop (bit-identical iterates) with, per iteration: primal forward, tangent
-// forward (gated GEMM, MODE 2), backward with the dcz / Delta accumulation fused into its epilogue,
-// and one weight-gradient GEMM per Wz_l (reduction over the batch, split over a thread-block cluster
-// and reduced through distributed shared memory -- no atomics, deterministic).
+// Pass 1 runs the GD loop to y_N (deterministic kernels), a = loss_scale (y_N - trueY); pass 2 replays
+// the same loop (bit-identical iterates) with, per iteration: primal forward, tangent forward (the same
+// gated product with the activation pattern of the primal Z_l), backward with the dcz / Delta
+// accumulation fused into its epilogue, and one weight-gradient GEMM per Wz_l (reduction over the
+// batch, split over a thread-block cluster and reduced through distributed shared memory -- no
+// atomics, deterministic).  The three gated products run on the tcgen05 3xTF32 kernel
+// (picnn_tc.cu, GDB instantiation) once the batch fills a 128-row tile, else on the FP32 FFMA
+// kernel (gated_gemm.cuh, MODE 0 / 2 / 1); the weight-gradient GEMM is FP32 FFMA in both cases.
 #include "gated_gemm.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 namespace icnn {
 
 size_t picnn_simt_ws_floats(const icnn_picnn* h, int B, size_t* zoff, size_t* doff);
+size_t picnn_gdb_tc_ws_floats(const icnn_picnn* h, int B, GdbTcBufs* b, float* base);
+void picnn_gdb_tc_gate_a(const icnn_picnn* h, const icnn_gates* gt, const float* a, const GdbTcBufs& b, cudaStream_t st);
+int picnn_gdb_tc_forward(const icnn_picnn* h, const icnn_gates* gt, const GdbTcBufs& b, bool tangent, cudaStream_t st);
+int picnn_gdb_tc_backward_layer(const icnn_picnn* h, const icnn_gates* gt, const GdbTcBufs& b, int i, int cur,
+                                const icnn_gd_grads* gr, float kappa, cudaStream_t st);
 void out_layer_launch(const icnn_picnn* h, const icnn_gates* gt, const float* Zlast, const float* y32, float* f,
                       float* delta, float* delta_hi, float* delta_lo, float* g, long long g_row_stride,
                       const int* perm, const int* count, int KS, const int* skip, cudaStream_t st);
@@ -174,8 +183,16 @@ __global__ void mse_grad_kernel(float* a, const float* y, const float* trueY, fl
 }
 
 struct GdbLayout {
-  size_t Z[ICNN_MAX_LAYERS], Zt[ICNN_MAX_LAYERS], Dacc[ICNN_MAX_LAYERS], dl[2], y, v, g, a, f, total;
+  size_t Z[ICNN_MAX_LAYERS], Zt[ICNN_MAX_LAYERS], Dacc[ICNN_MAX_LAYERS], dl[2], y, v, g, a, f, tc, total;
+  bool use_tc;
 };
+
+// tensor-core GEMMs (3xTF32) for the forward / tangent / backward products once a 128-row tile fills;
+// ICNN_GDB=simt keeps the FP32 FFMA kernels
+static bool gdb_use_tc(const icnn_picnn* h, int B) {
+  const char* v = getenv("ICNN_GDB");
+  return h->use_tc && B >= 64 && !(v && v[0] == 's');
+}
 
 static GdbLayout gdb_layout(const icnn_picnn* h, int B) {
   GdbLayout lo{};
@@ -191,6 +208,9 @@ static GdbLayout gdb_layout(const icnn_picnn* h, int B) {
   lo.dl[0] = take((size_t)B * smax); lo.dl[1] = take((size_t)B * smax);
   lo.y = take((size_t)B * h->n); lo.v = take((size_t)B * h->n); lo.g = take((size_t)B * h->n);
   lo.a = take((size_t)B * h->n); lo.f = take((size_t)B);
+  lo.tc = off;
+  lo.use_tc = gdb_use_tc(h, B);
+  if (lo.use_tc) off += picnn_gdb_tc_ws_floats(h, B, nullptr, nullptr);
   lo.total = off;
   return lo;
 }
@@ -210,7 +230,15 @@ static int gdb_iteration(const icnn_picnn* h, const icnn_gates* gt, float* ws, c
   const int B = gt->B, n = h->n, L = h->L;
   float* y = ws + lo.y; float* g = ws + lo.g; float* f = ws + lo.f; float* av = ws + lo.a;
   float* dl[2] = {ws + lo.dl[0], ws + lo.dl[1]};
-  for (int i = 0; i < L; ++i) {
+  GdbTcBufs tb{};
+  if (lo.use_tc) {
+    tb.y = y; tb.g = g; tb.dp[0] = dl[0]; tb.dp[1] = dl[1];
+    for (int i = 0; i < L; ++i) { tb.Z[i] = ws + lo.Z[i]; tb.Zt[i] = ws + lo.Zt[i]; tb.Dacc[i] = ws + lo.Dacc[i]; }
+    picnn_gdb_tc_ws_floats(h, B, &tb, ws + lo.tc);
+    int rc = picnn_gdb_tc_forward(h, gt, tb, acc != nullptr, st);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < L && !lo.use_tc; ++i) {
     GemmArgs a{};
     a.M = B; a.N = h->hidden[i]; a.K0 = h->prev(i); a.K1 = n;
     a.A0 = i ? ws + lo.Z[i - 1] : nullptr; a.G0 = i ? gt->cz[i] : nullptr; a.lda0 = a.K0;
@@ -223,7 +251,8 @@ static int gdb_iteration(const icnn_picnn* h, const icnn_gates* gt, float* ws, c
       GDB_LAUNCH(launch_gemm<2>(a, st), "gd_backward tangent");
     }
   }
-  out_layer_launch(h, gt, ws + lo.Z[L - 1], y, f, dl[0], nullptr, nullptr, g, n, nullptr, nullptr, 0, nullptr, st);
+  out_layer_launch(h, gt, ws + lo.Z[L - 1], y, f, dl[0], lo.use_tc ? tb.dh[0] : nullptr, lo.use_tc ? tb.dl[0] : nullptr,
+                   g, n, nullptr, nullptr, 0, nullptr, st);
   const int sl = h->hidden[L - 1];
   const long long NL = (long long)B * sl;
   if (acc) {
@@ -243,6 +272,12 @@ static int gdb_iteration(const icnn_picnn* h, const icnn_gates* gt, float* ws, c
       w.M = h->prev(i); w.N = h->hidden[i]; w.Kb = B; w.A = ws + lo.Zt[i - 1]; w.G = gt->cz[i]; w.lda = w.M;
       w.D = dl[cur]; w.ldd = w.N; w.C = acc->gr->dWz[i]; w.ldc = w.N; w.kappa = acc->kappa;
       GDB_LAUNCH(launch_wgrad(w, st), "gd_backward wgrad");
+    }
+    if (lo.use_tc) {
+      int rc = picnn_gdb_tc_backward_layer(h, gt, tb, i, cur, acc ? acc->gr : nullptr, acc ? acc->kappa : 0.f, st);
+      if (rc) return rc;
+      cur ^= 1;
+      continue;
     }
     GemmArgs a{};
     a.M = B; a.N0 = h->prev(i); a.N = a.N0 + n; a.K0 = h->hidden[i]; a.K1 = 0;
@@ -319,6 +354,11 @@ extern "C" int icnn_gd_backward(const icnn_picnn_t* h, const icnn_gates* gates, 
     if (pass == 0) {
       ICNN_CUDA_CHECK(cudaMemcpyAsync(yN, ws + lo.y, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
       mse_grad_kernel<<<gN, 256, 0, st>>>(ws + lo.a, ws + lo.y, trueY, loss_scale, N);
+      if (lo.use_tc) {
+        GdbTcBufs tb{};
+        picnn_gdb_tc_ws_floats(h, B, &tb, ws + lo.tc);
+        picnn_gdb_tc_gate_a(h, gates, ws + lo.a, tb, st);
+      }
     }
   }
 

@@ -146,6 +146,10 @@ struct TcArgs {
   const float* Cy; float* g; long long g_row_stride; const int* perm; const int* count; int KS; int n;
   float g_scale;
   float* C;  // mode 2
+  // GD training backward (GDB instantiation only, gd_backward.cu):
+  //   mode 0 with tangent != 0: Z = act'(D) o acc (D holds the primal activation), no bias
+  //   mode 1: optional plain copy of delta_prev, dCz += kappa * Ztprev o acc, Dacc += kappa * delta_prev
+  int tangent; float* dprev_plain; float* dCz; const float* Ztprev; float* Dacc; float kappa;
   // mode 3 (x-path gate GEMM): out = acc + bias[col]; up to 4 column ranges [rbeg[r], rbeg[r+1]) each with
   // its own ReLU flag and destination (row pitch rld[r]); range 0 may instead be written as a TF32
   // hi/lo pair (the next u-layer operand)
@@ -166,7 +170,7 @@ struct TcSmem {
 // <128,3>: one CTA / SM (198 KB);  <64,4>: one CTA / SM, deeper ring for small grids;
 // <64,2>: two CTAs / SM (98 KB each, 2 x 256 TMEM columns) so that one CTA's epilogue overlaps
 // the other's main loop.
-template <int BN, int NST_>
+template <int BN, int NST_, bool GDB = false>
 __global__ void __launch_bounds__(192, (BN == 64 && NST_ == 2) ? 2 : 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, TcArgs a) {
@@ -303,8 +307,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           for (int qq = 0; qq < S; ++qq) acc += *cl.map_shared_rank(P + rr * PP + c, qq);
           if (a.mode == 0) {
             const long long idx = (long long)m * a.N + nn;
-            const float x = acc + __ldg(a.D + idx);
-            const float z = x > 0.f ? x : a.alpha * x;
+            const float dv = __ldg(a.D + idx);
+            const float x = acc + dv;
+            float z = x > 0.f ? x : a.alpha * x;
+            if constexpr (GDB) { if (a.tangent) z = (dv > 0.f ? 1.f : a.alpha) * acc; }
             a.Z[idx] = z;
             if (a.nxt_hi) {
               const float p = z * __ldg(a.Cz_next + idx);
@@ -320,6 +326,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               const float h = tf32_hi(p);
               a.dprev_hi[(long long)m * a.dprev_ld + nn] = h;
               a.dprev_lo[(long long)m * a.dprev_ld + nn] = tf32_lo(p, h);
+              if constexpr (GDB) {
+                if (a.dprev_plain) a.dprev_plain[idx] = p;
+                if (a.dCz) {
+                  a.dCz[idx] = fmaf(a.kappa * __ldg(a.Ztprev + idx), acc, a.dCz[idx]);
+                  a.Dacc[idx] = fmaf(a.kappa, p, a.Dacc[idx]);
+                }
+              }
             } else {
               const int e = nn - a.N0;
               grow[e] = fmaf(a.g_scale * __ldg(a.Cy + (long long)m * a.n + e), acc, grow[e]);
@@ -356,6 +369,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       for (int r0 = 0; r0 < 32; r0 += RG) {
         if (m0 + q * 32 + r0 >= a.M) break;              // warp-uniform
         float acc[RG], in0[RG], in1[RG];
+        float in2[GDB ? RG : 1], in3[GDB ? RG : 1], in4[GDB ? RG : 1];
         unsigned long long gp[RG];
 #pragma unroll
         for (int i = 0; i < RG; ++i) {
@@ -375,6 +389,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 const long long idx = (long long)m * a.N0 + nn;
                 in0[i] = __ldg(a.Zprev + idx);
                 in1[i] = __ldg(a.Cz + idx);
+                if constexpr (GDB) {
+                  if (a.dCz) { in2[i] = __ldg(a.Ztprev + idx); in3[i] = a.dCz[idx]; in4[i] = a.Dacc[idx]; }
+                }
               } else {
                 const int e = nn - a.N0;
                 in0[i] = __ldg(a.Cy + (long long)m * a.n + e);
@@ -390,7 +407,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           if (a.mode == 0) {
             const long long idx = (long long)m * a.N + nn;
             const float x = acc[i] + in0[i];
-            const float z = x > 0.f ? x : a.alpha * x;
+            float z = x > 0.f ? x : a.alpha * x;
+            if constexpr (GDB) { if (a.tangent) z = (in0[i] > 0.f ? 1.f : a.alpha) * acc[i]; }
             a.Z[idx] = z;
             if (a.nxt_hi) {
               const float p = z * in1[i];
@@ -405,6 +423,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               const float h = tf32_hi(p);
               a.dprev_hi[(long long)m * a.dprev_ld + nn] = h;
               a.dprev_lo[(long long)m * a.dprev_ld + nn] = tf32_lo(p, h);
+              if constexpr (GDB) {
+                const long long idx = (long long)m * a.N0 + nn;
+                if (a.dprev_plain) a.dprev_plain[idx] = p;
+                if (a.dCz) {
+                  a.dCz[idx] = fmaf(a.kappa * in2[i], acc[i], in3[i]);
+                  a.Dacc[idx] = fmaf(a.kappa, p, in4[i]);
+                }
+              }
             } else {
               const int e = nn - a.N0;
               reinterpret_cast<float*>(gp[i])[e] = fmaf(a.g_scale * in0[i], acc[i], in1[i]);
@@ -529,12 +555,12 @@ static int make_tmap(CUtensorMap* tm, const float* base, long long rows, long lo
   return ICNN_OK;
 }
 
-template <int BN, int NST_>
+template <int BN, int NST_, bool GDB = false>
 static cudaError_t launch_tc_variant(const CUtensorMap& tAh, const CUtensorMap& tAl, const CUtensorMap& tBh,
                                      const CUtensorMap& tBl, const TcArgs& a, int splitk, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, NST_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, NST_, GDB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TcSmem<BN, NST_>::TOTAL);
     if (e != cudaSuccess) return e;
     attr = true;
@@ -548,11 +574,11 @@ static cudaError_t launch_tc_variant(const CUtensorMap& tAh, const CUtensorMap& 
   lattr[0].id = cudaLaunchAttributeClusterDimension;
   lattr[0].val.clusterDim.x = 1; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = splitk;
   cfg.attrs = lattr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, NST_>, tAh, tAl, tBh, tBl, a);
+  return cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, NST_, GDB>, tAh, tAl, tBh, tBl, a);
 }
 
 static int launch_tc_gemm(const float* Ah, const float* Al, long long lda, const float* Bh, const float* Bl, long long ldb,
-                          TcArgs a, cudaStream_t st) {
+                          TcArgs a, cudaStream_t st, bool gdb = false) {
   const int gy = cdiv(a.M, TC_BM);
   // tile choice: 64-wide tiles; two CTAs per SM (the epilogue of one overlaps the main loop of the
   // other) once there are >= 2 tiles per SM, else one CTA per SM with a 4-deep ring.
@@ -563,6 +589,7 @@ static int launch_tc_gemm(const float* Ah, const float* Al, long long lda, const
   if (const char* v = getenv("ICNN_TC_CFG")) {
     if (!strcmp(v, "128")) cfg = 0; else if (!strcmp(v, "64x4")) cfg = 1; else if (!strcmp(v, "64x2")) cfg = 2;
   }
+  if (gdb && cfg == 0) cfg = 1;
   const int BN = cfg == 0 ? 128 : 64;
   CUtensorMap tAh, tAl, tBh, tBl;
   int rc;
@@ -577,9 +604,14 @@ static int launch_tc_gemm(const float* Ah, const float* Al, long long lda, const
     while (splitk < 8 && tiles * splitk * 2 <= 148 && nkb / (splitk * 2) >= 4) splitk *= 2;
     if (const char* v = getenv("ICNN_TC_SPLITK")) { const int w = atoi(v); if (w == 1 || w == 2 || w == 4 || w == 8) splitk = w; }
   }
-  cudaError_t e = cfg == 0 ? launch_tc_variant<128, 3>(tAh, tAl, tBh, tBl, a, 1, st)
-                : cfg == 1 ? launch_tc_variant<64, 4>(tAh, tAl, tBh, tBl, a, splitk, st)
-                           : launch_tc_variant<64, 2>(tAh, tAl, tBh, tBl, a, 1, st);
+  cudaError_t e;
+  if (gdb)   // GD training backward: the 64-wide variants with the tangent / accumulation epilogue
+    e = cfg == 2 ? launch_tc_variant<64, 2, true>(tAh, tAl, tBh, tBl, a, 1, st)
+                 : launch_tc_variant<64, 4, true>(tAh, tAl, tBh, tBl, a, cfg == 1 ? splitk : 1, st);
+  else
+    e = cfg == 0 ? launch_tc_variant<128, 3>(tAh, tAl, tBh, tBl, a, 1, st)
+      : cfg == 1 ? launch_tc_variant<64, 4>(tAh, tAl, tBh, tBl, a, splitk, st)
+                 : launch_tc_variant<64, 2>(tAh, tAl, tBh, tBl, a, 1, st);
   if (e != cudaSuccess) { set_error("tc_gemm launch: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
   return ICNN_OK;
 }
@@ -686,6 +718,76 @@ int picnn_fg_tc(const icnn_picnn* h, const icnn_gates* gt, const float* y32, flo
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("picnn_fg_tc launch: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
   return ICNN_OK;
+}
+
+// ---- GD training backward on the tensor-core GEMMs (gd_backward.cu orchestrates) -----------------------
+size_t picnn_gdb_tc_ws_floats(const icnn_picnn* h, int B, GdbTcBufs* b, float* base) {
+  size_t off = 0;
+  auto take = [&](size_t nfl) { size_t o = off; off += (nfl + 63) & ~(size_t)63; return base ? base + o : nullptr; };
+  int smax = 0;
+  for (int i = 0; i < h->L; ++i) {
+    const size_t sz = (size_t)B * ld4(h->prev(i) + h->n);
+    float* p0 = take(sz); float* p1 = take(sz); float* p2 = take(sz); float* p3 = take(sz);
+    if (b) { b->Ah[i] = p0; b->Al[i] = p1; b->Ath[i] = p2; b->Atl[i] = p3; }
+    smax = h->hidden[i] > smax ? h->hidden[i] : smax;
+  }
+  for (int j = 0; j < 2; ++j) {
+    float* p0 = take((size_t)B * ld4(smax)); float* p1 = take((size_t)B * ld4(smax));
+    if (b) { b->dh[j] = p0; b->dl[j] = p1; }
+  }
+  return off;
+}
+
+static void gdb_gate(const icnn_picnn* h, const icnn_gates* gt, const float* v, float* const* hi, float* const* lo,
+                     cudaStream_t st) {
+  GateYArgs ga{};
+  ga.B = gt->B; ga.n = h->n; ga.L = h->L; ga.y = v; ga.sc = 1.f; ga.sh = 0.f; ga.skip_if_zero = nullptr;
+  for (int i = 0; i < h->L; ++i) {
+    ga.cy[i] = gt->cy[i]; ga.hi[i] = hi[i]; ga.lo[i] = lo[i]; ga.ld[i] = ld4(h->prev(i) + h->n); ga.off[i] = h->prev(i);
+  }
+  const long long N = (long long)gt->B * h->n;
+  gate_y_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ga);
+}
+
+// the (a o cy_i) columns of the tangent operands: constant over the GD iterations
+void picnn_gdb_tc_gate_a(const icnn_picnn* h, const icnn_gates* gt, const float* a, const GdbTcBufs& b, cudaStream_t st) {
+  gdb_gate(h, gt, a, b.Ath, b.Atl, st);
+}
+
+// primal forward of every hidden layer at b.y (and, with tangent, the tangent layers on direction a)
+int picnn_gdb_tc_forward(const icnn_picnn* h, const icnn_gates* gt, const GdbTcBufs& b, bool tangent, cudaStream_t st) {
+  const int B = gt->B, n = h->n, L = h->L;
+  gdb_gate(h, gt, b.y, b.Ah, b.Al, st);
+  for (int i = 0; i < L; ++i) {
+    TcArgs a{};
+    a.M = B; a.N = h->hidden[i]; a.K = h->prev(i) + n; a.mode = 0;
+    a.D = gt->d[i]; a.Z = b.Z[i]; a.alpha = h->alpha;
+    if (i + 1 < L) { a.Cz_next = gt->cz[i + 1]; a.nxt_hi = b.Ah[i + 1]; a.nxt_lo = b.Al[i + 1]; a.nxt_ld = ld4(h->hidden[i] + n); }
+    int rc = launch_tc_gemm(b.Ah[i], b.Al[i], ld4(a.K), h->Wf_hi[i], h->Wf_lo[i], ld4(a.K), a, st, true);
+    if (rc) return rc;
+    if (tangent) {
+      a.tangent = 1; a.D = b.Z[i]; a.Z = b.Zt[i];
+      if (i + 1 < L) { a.nxt_hi = b.Ath[i + 1]; a.nxt_lo = b.Atl[i + 1]; }
+      rc = launch_tc_gemm(b.Ath[i], b.Atl[i], ld4(a.K), h->Wf_hi[i], h->Wf_lo[i], ld4(a.K), a, st, true);
+      if (rc) return rc;
+    }
+  }
+  return ICNN_OK;
+}
+
+// backward GEMM of hidden layer i: delta_i (hi/lo in slot cur) -> delta_{i-1} (slot cur^1: hi/lo + plain) and g;
+// with gr, dcz_i += kappa zt_{i-1} o (delta_i Wz_i^T) and Delta_{i-1} += kappa delta_{i-1} in the epilogue
+int picnn_gdb_tc_backward_layer(const icnn_picnn* h, const icnn_gates* gt, const GdbTcBufs& b, int i, int cur,
+                                const icnn_gd_grads* gr, float kappa, cudaStream_t st) {
+  TcArgs a{};
+  a.M = gt->B; a.N0 = h->prev(i); a.N = a.N0 + h->n; a.K = h->hidden[i]; a.mode = 1; a.alpha = h->alpha;
+  a.Zprev = i ? b.Z[i - 1] : nullptr; a.Cz = i ? gt->cz[i] : nullptr;
+  a.dprev_hi = b.dh[cur ^ 1]; a.dprev_lo = b.dl[cur ^ 1]; a.dprev_ld = ld4(a.N0);
+  a.Cy = gt->cy[i]; a.g = b.g; a.g_row_stride = h->n; a.n = h->n; a.g_scale = 1.f;
+  if (gr && i > 0) {
+    a.dprev_plain = b.dp[cur ^ 1]; a.dCz = gr->dcz[i]; a.Ztprev = b.Zt[i - 1]; a.Dacc = b.Dacc[i - 1]; a.kappa = kappa;
+  }
+  return launch_tc_gemm(b.dh[cur], b.dl[cur], ld4(a.K), h->Wb_hi[i], h->Wb_lo[i], ld4(a.K), a, st, true);
 }
 
 // ---- x-path (gate precompute) -------------------------------------------

@@ -1,9 +1,10 @@
 """d mse / d theta through the unrolled momentum-GD loop (multi-label-cls/icnn-back.py:116-139) on the
 GPU vs the torch-autograd golden vectors and the float64 numpy restatement.
 
-Tolerance: the device path is float32 (FFMA GEMMs, float32 accumulation over the batch and the
-nIter iterations); every gradient array must agree with the float64 reference to 2e-4 of that
-array's largest entry where no ReLU kink flips (measured 1e-6: profiles/r01_gd_grad.md)."""
+Tolerance: the device path is float32 (3xTF32 tcgen05 or FFMA GEMMs, float32 accumulation over the
+batch and the nIter iterations); every gradient array must agree with the float64 reference to 2e-4
+of that array's largest entry on the samples whose iterates cross no ReLU kink differently
+(measured 1e-6 .. 5e-5: profiles/r01_gd_grad.md)."""
 import os
 
 import numpy as np
@@ -15,7 +16,6 @@ from icnn_b200.workloads import synth_params
 pytestmark = pytest.mark.gpu
 
 RTOL = 2e-4
-PTOL = 5e-3   # parameter gradients when kink flips are possible (see test_matches_oracle)
 
 
 def relerr(a, b):
@@ -61,40 +61,64 @@ def _dims_case(m, n, hidden, B, seed):
     ((12, 37, [50, 21, 33]), 77, 10, 0.02, 0.5),       # odd widths, three hidden layers, ragged tiles
 ])
 def test_matches_oracle(dims, B, nIter, lr, mom):
+    """A float32 / 3xTF32 iterate that lands on the other side of a ReLU kink changes that sample's
+    gradient by O(1) for a step (the sensitivity DESIGN.md section 4 describes for the bundle path;
+    reproduced inside the float64 oracle by a 5e-6 relative perturbation of W^y: 3 of 200 rows move,
+    parameter gradients by 1e-2).  Such rows are identified from y_N and the per-sample gate adjoints
+    (<= 2 % of the batch), dropped from the minibatch, and both sides are run again: on the remaining
+    rows every gradient array must agree to RTOL of its largest entry."""
     import icnn_b200
     m, n, hidden = dims
     p, x, y0, tY = _dims_case(m, n, hidden, B, seed=21)
-    gts = picnn_np.gates(p, x)
-    yo, go = gd_grad_np.gd_backward(p, gts, y0, nIter, lr, mom, lambda y: 2.0 * (y - tY) / y.size)
-    xo = gd_grad_np.xpath_backward(p, x, go["dcy"], go["dcz"])
     net = icnn_b200.PICNN.from_params(p)
-    yN, gr = icnn_b200.gd_grad.gd_grad(net.bind(x), y0, tY, nIter=nIter, lr=lr, momentum=mom, x=x)
-    # a float32 iterate that lands on the other side of a ReLU kink changes that sample's gradient by
-    # O(1) for one step (the long-horizon sensitivity DESIGN.md section 4 describes for the bundle
-    # path): y_N and the per-sample gate adjoints are compared row-wise, >= 99 % of the samples within
-    # tolerance; the parameter gradients (sums over the batch) absorb the few flipped rows
-    dy = np.abs(yN - yo).max(axis=1)
-    assert np.median(dy) < 2e-6 and np.mean(dy < 1e-4) >= 0.99, (np.median(dy), dy.max())
-    errs, rows = {}, {}
-
-    def rowfrac(a, b):
-        d = np.abs(np.asarray(a, dtype=np.float64) - b).max(axis=1) / max(np.abs(b).max(), 1e-30)
-        return float(np.mean(d < RTOL))
-
+    keep = np.arange(B)
+    dropped = 0
+    for attempt in range(4):
+        xs, ys, ts = x[keep], y0[keep], tY[keep]
+        scale = 2.0 / tY.size          # the same loss weight per sample on every attempt
+        yo, go = gd_grad_np.gd_backward(p, picnn_np.gates(p, xs), ys, nIter, lr, mom, lambda y: scale * (y - ts))
+        xo = gd_grad_np.xpath_backward(p, xs, go["dcy"], go["dcz"])
+        yN, gr = icnn_b200.gd_grad.gd_grad(net.bind(xs), ys, ts, nIter=nIter, lr=lr, momentum=mom, x=xs,
+                                           loss_scale=scale)
+        bad = np.abs(yN - yo).max(axis=1) >= 1e-4
+        for l in range(p.L + 1):
+            for k in ("dcy", "dcz"):
+                if go[k][l] is not None:
+                    d = np.abs(gr[k][l].astype(np.float64) - go[k][l]).max(axis=1) / max(np.abs(go[k][l]).max(), 1e-30)
+                    bad |= d >= RTOL
+        if not bad.any():
+            break
+        dropped += int(bad.sum())
+        keep = keep[~bad]
+    assert not bad.any() and dropped <= 0.02 * B, (dropped, B)
+    assert np.median(np.abs(yN - yo).max(axis=1)) < 2e-6
+    errs = {}
     for l in range(p.L + 1):
         errs["Wy%d" % l] = relerr(gr["Wy"][l], go["dWy"][l])
-        rows["dcy%d" % l] = rowfrac(gr["dcy"][l], go["dcy"][l])
         errs["Wyu%d" % l] = relerr(gr["Wyu"][l], xo["dWyu"][l])
         if l > 0:
             errs["Wz%d" % l] = relerr(gr["Wz"][l], go["dWz"][l])
-            rows["dcz%d" % l] = rowfrac(gr["dcz"][l], go["dcz"][l])
             errs["Wzu%d" % l] = relerr(gr["Wzu"][l], xo["dWzu"][l])
     for l in range(p.L):
         errs["Wu%d" % l] = relerr(gr["Wu"][l], xo["dWu"][l])
-    print(dims, "dy max %.2e" % dy.max(), "param max rel err %.2e" % max(errs.values()), max(errs, key=errs.get),
-          "min row fraction %.4f" % min(rows.values()), errs)
-    assert min(rows.values()) >= 0.99, rows
-    assert max(errs.values()) < PTOL, errs
+    print(dims, "rows dropped (kink flips)", dropped, "of", B, "param max rel err %.2e" % max(errs.values()),
+          max(errs, key=errs.get))
+    assert max(errs.values()) < RTOL, errs
+
+
+def test_ffma_and_tensor_core_paths_agree(monkeypatch):
+    """ICNN_GDB=simt keeps the three gated products on the FP32 FFMA kernel (the accuracy anchor)."""
+    import icnn_b200
+    p, x, y0, tY = _dims_case(40, 64, [96, 80], 256, seed=5)
+    fg = icnn_b200.PICNN.from_params(p).bind(x)
+    y_tc, g_tc = icnn_b200.gd_grad.gd_grad(fg, y0, tY, nIter=5, lr=0.02, momentum=0.5)
+    monkeypatch.setenv("ICNN_GDB", "simt")
+    y_ff, g_ff = icnn_b200.gd_grad.gd_grad(fg, y0, tY, nIter=5, lr=0.02, momentum=0.5)
+    assert np.abs(y_tc - y_ff).max() < 1e-5
+    for k in ("Wy", "Wz", "dcy", "dcz"):
+        for a, b in zip(g_tc[k], g_ff[k]):
+            if a is not None:
+                assert relerr(a, b.astype(np.float64)) < 5e-5, k
 
 
 def test_yn_is_the_gd_solve_iterate():
