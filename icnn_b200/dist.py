@@ -1,5 +1,7 @@
 """Sample-sharded multi-GPU inner loop: one process per GPU, no data-path collective except a
-single all-gather of the solved y* at the end.
+single all-gather of the solved y* at the end.  The training backward of the
+unrolled GD loop (``gd_grad_sharded``) has one real exchange step: the parameter gradients are sums
+over samples, so they take one bucketed all-reduce; per-sample adjoints stay sharded.
 
 Every sample's bundle, dual solve and iterate are independent (the reference loops
 ``for u in range(bsize)``, lib/bundle_entropy.py:211), so rows are split into contiguous blocks,
@@ -57,3 +59,38 @@ def solve_batch_sharded(net, x, y0, nIter=None, solver="pc", variant="lib", affi
     st = out[-1]
     y_all = allgather_rows(st.y, B, group=group)
     return y_all, out[:-1]
+
+
+PARAM_KEYS = ("Wy", "Wz", "Wu", "bu", "Wzu", "bzu", "Wyu", "byu")
+
+
+def allreduce_grads(grads, keys=PARAM_KEYS, group=None):
+    """Sum the parameter gradients over ranks with ONE all-reduce: every tensor of ``grads[k]``
+    (k in keys, None entries skipped) is packed into a single flat bucket (NVSwitch collectives are
+    latency- not link-bound, so one launch beats one per tensor), reduced, and unpacked in place."""
+    ts = [t for k in keys if k in grads for t in grads[k] if t is not None]
+    if not ts:
+        return grads
+    flat = torch.cat([t.reshape(-1) for t in ts])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for t in ts:
+        t.copy_(flat[off:off + t.numel()].view_as(t))
+        off += t.numel()
+    return grads
+
+
+def gd_grad_sharded(net, x, y0, trueY, nIter=30, lr=0.01, momentum=0.3, group=None):
+    """d mse / d theta through the unrolled GD loop (icnn_b200.gd_grad) for a global minibatch split
+    into contiguous row blocks: rank-local ``icnn_gd_backward`` with the GLOBAL loss weight
+    2/(B n), one all-reduce of the parameter gradients, one all-gather of y_N.  Returns
+    (yN_all [B, n] CUDA tensor, grads) -- grads['dcy'/'dcz'] cover this rank's rows only."""
+    from . import gd_grad as _gd
+    rank, ws = dist.get_rank(group), dist.get_world_size(group)
+    B = x.shape[0]
+    lo, hi = shard_rows(B, rank, ws)
+    fg = net.bind(x[lo:hi])
+    yN, gr = _gd.gd_grad(fg, y0[lo:hi], trueY[lo:hi], nIter=nIter, lr=lr, momentum=momentum,
+                         loss_scale=2.0 / (B * net.n), x=x[lo:hi], return_device=True)
+    allreduce_grads(gr, group=group)
+    return allgather_rows(yN, B, group=group), gr

@@ -56,3 +56,38 @@ def test_allgather_rows_gloo(ws, B):
     for p in procs:
         p.join(timeout=60)
     assert sorted(r for r, _ in res) == list(range(ws)) and all(ok for _, ok in res)
+
+
+def _worker_grads(rank, ws, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        v = float(rank + 1)
+        grads = {"Wy": [torch.full((3, 2), v), torch.full((3, 1), 2 * v)], "Wz": [None, torch.full((2, 1), -v)],
+                 "bu": [torch.full((4,), 0.5 * v)], "dcy": [torch.full((5, 3), v)]}    # dcy: per-sample, not reduced
+        idist.allreduce_grads(grads)
+        tot = sum(range(1, ws + 1))
+        ok = (torch.equal(grads["Wy"][0], torch.full((3, 2), float(tot))) and
+              torch.equal(grads["Wy"][1], torch.full((3, 1), 2.0 * tot)) and
+              torch.equal(grads["Wz"][1], torch.full((2, 1), -float(tot))) and
+              torch.equal(grads["bu"][0], torch.full((4,), 0.5 * tot)) and
+              torch.equal(grads["dcy"][0], torch.full((5, 3), v)) and grads["Wz"][0] is None)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ws", [2, 3])
+def test_allreduce_grads_gloo(ws):
+    """The one exchange step of the sharded training backward: a single bucketed SUM all-reduce of the
+    parameter gradients; per-sample adjoints are left alone."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_grads, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(ws)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r for r, _ in res) == list(range(ws)) and all(ok for _, ok in res)
