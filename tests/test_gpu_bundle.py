@@ -225,6 +225,37 @@ def test_fused_properties_at_full_size():
         np.testing.assert_allclose(G[u][-1], gchk[u], rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("name", ["C2", "C4", "T", "C5"])
+def test_fused_properties_at_full_size_other_configs(name):
+    """BASELINE.json's remaining configs (and the north-star target shape) at their FULL sizes --
+    C2 400 x 2048 x 30 its, C4 65 536 x 6 (RL variant), T 4096 x 512 x 10, C5 8192 x 4096 x 50 --
+    through size-independent properties: finite iterate inside the box (RL: inside the clip
+    [.03, .97], RL/src/bundle_entropy.py:118), multipliers on the simplex, every kept row an
+    under-estimator of the convex f at y*, bookkeeping lists consistent."""
+    import icnn_b200
+    from icnn_b200 import bundle_entropy as be
+    cfg = synth.CONFIGS[name]
+    p, x, y0 = synth.make_inputs(name)
+    B, n, nIter = cfg["B"], cfg["n"], cfg["nIter"]
+    net = icnn_b200.PICNN.from_params(p)
+    fg = net.bind(x, affine=cfg["affine"])
+    y, G, h, lam, ys, nIters = be.solveBatch(fg, y0.copy(), nIter=nIter, variant=cfg["variant"])
+    assert y.shape == (B, n) and np.all(np.isfinite(y))
+    if cfg["variant"] == "rl":
+        assert y.min() >= 0.03 - 1e-12 and y.max() <= 0.97 + 1e-12
+    else:
+        assert y.min() > 0 and y.max() < 1
+    assert len(G) == B and len(nIters) == B
+    f_star, _ = fg(y)
+    step = max(1, B // 41)
+    for u in range(0, B, step):
+        k = len(G[u])
+        assert 1 <= k <= min(nIter, n) + 1 and len(h[u]) == k and len(ys[u]) == k and lam[u].shape == (k,)
+        assert np.all(lam[u] >= 0) and abs(lam[u].sum() - 1) < 1e-6
+        Gu = np.array(G[u], dtype=np.float64)
+        assert np.all(Gu.dot(y[u]) + np.array(h[u]) <= f_star[u] + 1e-3 * max(1, abs(f_star[u])))
+
+
 def test_edge_cases_and_error_paths():
     import icnn_b200
     from icnn_b200 import bundle_entropy as be
