@@ -413,6 +413,41 @@ def run_gpu(args):
                    "value": cT["B"] * itsT / (msT * 1e-3), "unit": UNIT, "ms_per_step": msT, "iters_executed": itsT,
                    "n_gpus": 1}
         del stT, fgT, netT
+    # ---- secondary (C3 only; SURVEY.md section 8d config 3 asks for both inner loops): the 30-step
+    # momentum-GD loop (multi-label-cls/icnn-back.py:36-38 defaults) next to the bundle loop, the final
+    # mean f(y) - H(y) of each (what ebundle-vs-gd.py:94-99 plots), and the GD training backward ----
+    extra_gd = None
+    if args.workload == "C3" and world == 1 and not cfg["affine"]:
+        from icnn_b200 import gd as _gd, gd_grad as _gdg
+
+        def f_minus_h(y32):
+            f_, _ = fg.fg_device(y32.contiguous())
+            ent = -(y32 * torch.log(y32) + (1 - y32) * torch.log(1 - y32))
+            ent = torch.nan_to_num(ent, nan=0.0).sum(1)        # 0 log 0 = 0 (ebundle-vs-gd.py:38-41)
+            return float((f_ - ent).mean())
+
+        y0f = y0_dev.to(torch.float32)
+        tYd = (torch.rand(B, n, device=dev, generator=torch.Generator(device=dev).manual_seed(5)) < 0.1).float()
+
+        def timed(fn, reps=5):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0_.record()
+            for _ in range(reps):
+                r_ = fn()
+            e1_.record(); torch.cuda.synchronize()
+            return e0_.elapsed_time(e1_) / reps, r_
+
+        ms_gd, (y_gd, _f) = timed(lambda: _gd.solve(fg, y0f, nIter=30, lr=0.01, momentum=0.3, return_device=True))
+        ms_bw, _r = timed(lambda: _gdg.gd_grad(fg, y0f, tYd, nIter=30, lr=0.01, momentum=0.3, return_device=True))
+        step_device(); torch.cuda.synchronize()
+        extra_gd = {"gd_inner_loop": {"iters": 30, "lr": 0.01, "momentum": 0.3, "ms": ms_gd,
+                                      "value": B * 30 / (ms_gd * 1e-3), "unit": UNIT,
+                                      "mean_f_minus_H": f_minus_h(y_gd)},
+                    "bundle_inner_loop": {"iters": its, "mean_f_minus_H": f_minus_h(st.y.to(torch.float32))},
+                    "gd_training_backward_ms": ms_bw}
     if world > 1:
         dist.barrier()
     line = None
@@ -436,7 +471,7 @@ def run_gpu(args):
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clk.summary(), "roofline": dominant,
             "kernels": {"K1_picnn_fg": roof_k1, "K2_bundle_step": roof_k2},
-            "cpu_baseline": cpub, "target_shape": extra_T,
+            "cpu_baseline": cpub, "target_shape": extra_T, "gd_mode": extra_gd,
         }
         print(json.dumps(line))
     if world > 1:

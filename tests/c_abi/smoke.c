@@ -1,7 +1,8 @@
 /* Plain-C consumer of the C ABI (include/icnn_b200.h): no Python, no torch.
  * Builds a tiny PICNN (n=4, hidden [8], ReLU), evaluates f / df/dy through icnn_picnn_fg and checks
  * them against a straightforward host loop, then runs one bundle-entropy step and checks the
- * multipliers sum to one.  Compiled and run by tests/test_gpu_c_abi.py. */
+ * multipliers sum to one, then one step of the GD training backward against its closed form.
+ * Compiled and run by tests/test_gpu_c_abi.py. */
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -82,6 +83,35 @@ int main(void) {
       const double want = 1.0 / (1.0 + exp((double)g[b * N + e]));
       if (fabs(ynew[b * N + e] - want) > 1e-6) { printf("y mismatch %g %g\n", ynew[b * N + e], want); return 6; }
     }
+  }
+  /* training backward of ONE momentum-GD step through the ABI; the output layer has a closed form:
+   * y1 = y - lr (1+m) g(y), a = scale (y1 - trueY), dWy_L[e] = -lr (1+m) sum_b a[b,e] cy_L[b,e] */
+  {
+    const float lr = 0.1f, mom = 0.3f, scale = 2.0f / (B * N);
+    float zero[B * N] = {0};
+    float *tYd = dev(zero, B * N), *yNd, *dWy0, *dWy1, *dWz1, *dcy0, *dcy1, *dcz1;
+    CK(cudaMalloc((void**)&yNd, B * N * 4)); CK(cudaMalloc((void**)&dWy0, N * S * 4)); CK(cudaMalloc((void**)&dWy1, N * 4));
+    CK(cudaMalloc((void**)&dWz1, S * 4)); CK(cudaMalloc((void**)&dcy0, B * N * 4)); CK(cudaMalloc((void**)&dcy1, B * N * 4));
+    CK(cudaMalloc((void**)&dcz1, B * S * 4));
+    float* dWy[2] = {dWy0, dWy1}; float* dWz[2] = {NULL, dWz1}; float* dcy[2] = {dcy0, dcy1}; float* dcz[2] = {NULL, dcz1};
+    icnn_gd_grads gr = {dWy, dWz, dcy, dcz};
+    void* ws2; CK(cudaMalloc(&ws2, icnn_gd_backward_workspace_bytes(h, B) + 256));
+    RC(icnn_gd_backward(h, &gates, yd, tYd, scale, 1, lr, mom, yNd, &gr, ws2, NULL));
+    CK(cudaDeviceSynchronize());
+    float y1[B * N], gw[N];
+    CK(cudaMemcpy(y1, yNd, sizeof y1, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(gw, dWy1, sizeof gw, cudaMemcpyDeviceToHost));
+    double e1 = 0, e2 = 0;
+    for (int e = 0; e < N; ++e) {
+      double want = 0;
+      for (int b = 0; b < B; ++b) {
+        const double yy = (double)y[b * N + e] - (double)lr * (1.0 + mom) * g[b * N + e];
+        e1 = fmax(e1, fabs(yy - y1[b * N + e]));
+        want += -(double)lr * (1.0 + mom) * scale * yy * cy1[b * N + e];
+      }
+      e2 = fmax(e2, fabs(want - gw[e]));
+    }
+    printf("gd_backward: y1 err %.3e, dWy_L err %.3e\n", e1, e2);
+    if (!(e1 < 1e-5 && e2 < 1e-6)) return 7;
   }
   icnn_picnn_destroy(h);
   printf("C ABI OK\n");
