@@ -102,7 +102,7 @@ def _load():
                                     C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.icnn_argmin_grad.argtypes = [C.POINTER(BundleBufs), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.icnn_gd_backward_workspace_bytes.argtypes = [C.c_void_p, C.c_int32]
+    lib.icnn_gd_backward_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.icnn_gd_backward_workspace_bytes.restype = C.c_size_t
     lib.icnn_gd_backward.argtypes = [C.c_void_p, C.POINTER(Gates), C.c_void_p, C.c_void_p, C.c_float, C.c_int32,
                                      C.c_float, C.c_float, C.c_void_p, C.POINTER(GdGrads), C.c_void_p, C.c_void_p]

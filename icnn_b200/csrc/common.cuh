@@ -43,6 +43,13 @@ struct GdbTcBufs {
   float* Ah[ICNN_MAX_LAYERS]; float* Al[ICNN_MAX_LAYERS];     // primal K-concatenated operands (TF32 hi/lo)
   float* Ath[ICNN_MAX_LAYERS]; float* Atl[ICNN_MAX_LAYERS];   // tangent operands
   float* dh[2]; float* dl[2]; float* dp[2];                   // delta: hi / lo / plain, ping-pong
+  // backward-epilogue extras (all optional)
+  float* dstore[ICNN_MAX_LAYERS];   // plain delta_l goes here instead of dp[] (stored-pattern mode)
+  float* astore[ICNN_MAX_LAYERS];   // plain pre-gating product delta_l Wz_l^T
+  float* dcz[ICNN_MAX_LAYERS + 1];  // dcz_l += kappa zt_{l-1} o (delta_l Wz_l^T)
+  bool acc_delta;                   // Dacc_{l-1} += kappa delta_{l-1}
+  bool want_plain;                  // write plain delta_{l-1} (into dstore or dp)
+  float kappa;
 };
 
 }  // namespace icnn

@@ -46,7 +46,7 @@ __device__ __forceinline__ void epilogue_elem(const GemmArgs& a, int m, int nn, 
     a.Z[(long long)m * a.N + nn] = v > 0.f ? v : a.alpha * v;
   } else if (MODE == 2) {
     const long long idx = (long long)m * a.N + nn;
-    a.Z[idx] = (a.Zmask[idx] > 0.f ? 1.f : a.alpha) * acc;
+    a.Z[idx] = a.Zmask ? (a.Zmask[idx] > 0.f ? 1.f : a.alpha) * acc : acc;   // Zmask == nullptr: plain product
   } else {
     if (nn < a.N0) {
       const long long idx = (long long)m * a.N0 + nn;

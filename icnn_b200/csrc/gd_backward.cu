@@ -36,7 +36,9 @@ size_t picnn_gdb_tc_ws_floats(const icnn_picnn* h, int B, GdbTcBufs* b, float* b
 void picnn_gdb_tc_gate_a(const icnn_picnn* h, const icnn_gates* gt, const float* a, const GdbTcBufs& b, cudaStream_t st);
 int picnn_gdb_tc_forward(const icnn_picnn* h, const icnn_gates* gt, const GdbTcBufs& b, bool tangent, cudaStream_t st);
 int picnn_gdb_tc_backward_layer(const icnn_picnn* h, const icnn_gates* gt, const GdbTcBufs& b, int i, int cur,
-                                const icnn_gd_grads* gr, float kappa, cudaStream_t st);
+                                cudaStream_t st);
+int picnn_gdb_tc_stored_tangent(const icnn_picnn* h, int l, long long M, int B, const float* P_hi, const float* P_lo,
+                                const float* Ty, const float* Zs, float* Zt, cudaStream_t st);
 void out_layer_launch(const icnn_picnn* h, const icnn_gates* gt, const float* Zlast, const float* y32, float* f,
                       float* delta, float* delta_hi, float* delta_lo, float* g, long long g_row_stride,
                       const int* perm, const int* count, int KS, const int* skip, cudaStream_t st);
@@ -182,9 +184,57 @@ __global__ void mse_grad_kernel(float* a, const float* y, const float* trueY, fl
   if (i < N) a[i] = scale * (y[i] - trueY[i]);
 }
 
+// Stored-pattern phase, per (sample b, unit j of layer l-1), looping over the nIter stored iterations:
+//   zt_i = zt_{l-1}^(i)[b, j]   (layer 0: act'(Zs_0^(i)) * Ty_0, later layers: read from Zt_st)
+//   hidden layer l:  dcz_l[b, j] = sum_i kappa_i zt_i As_l^(i)[b, j];   P^(i)[b, j] = zt_i cz_l[b, j]
+//                    (TF32 hi/lo operand of the batched tangent GEMM, and kappa_i * P plain for the
+//                    batched weight-gradient GEMM)
+//   output layer:    S[b, j] = sum_i kappa_i zt_i;   dcz_L[b, j] = S wz_L[j]
+struct StageArgs {
+  int B, S, nIter; float alpha;
+  const float* kappa;        // device [nIter]
+  const float* Zs; const float* Ty;   // on-the-fly zt (layer 0) when Zt_st == nullptr
+  const float* Zt_st;
+  const float* As;           // hidden layer: stored delta_l Wz_l^T; nullptr = output layer
+  const float* cz; const float* wz;
+  float* dcz; float* Sout;
+  float* P_hi; float* P_lo; int ldp; float* Pk;
+};
+__global__ void tangent_stage_kernel(StageArgs a) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long BS = (long long)a.B * a.S;
+  if (idx >= BS) return;
+  const int b = (int)(idx / a.S), j = (int)(idx % a.S);
+  const float ty = a.Zt_st ? 0.f : a.Ty[idx];
+  const float czv = a.cz ? a.cz[idx] : 0.f;
+  float acc = 0.f;
+  for (int i = 0; i < a.nIter; ++i) {
+    const long long off = (long long)i * BS + idx;
+    const float zt = a.Zt_st ? a.Zt_st[off] : (a.Zs[off] > 0.f ? 1.f : a.alpha) * ty;
+    const float k = a.kappa[i];
+    if (a.As) {
+      acc = fmaf(k * zt, a.As[off], acc);
+      const float p = zt * czv;
+      const float h = __uint_as_float((__float_as_uint(p) + 0x00001000u) & 0xFFFFE000u);   // tf32_rn, as picnn_tc.cu
+      const long long o = ((long long)i * a.B + b) * a.ldp + j;
+      a.P_hi[o] = h;
+      a.P_lo[o] = __uint_as_float((__float_as_uint(p - h) + 0x00001000u) & 0xFFFFE000u);
+      a.Pk[off] = k * p;
+    } else {
+      acc = fmaf(k, zt, acc);
+    }
+  }
+  if (a.As) a.dcz[idx] = acc;
+  else { a.dcz[idx] = acc * a.wz[j]; a.Sout[idx] = acc; }
+}
+
 struct GdbLayout {
   size_t Z[ICNN_MAX_LAYERS], Zt[ICNN_MAX_LAYERS], Dacc[ICNN_MAX_LAYERS], dl[2], y, v, g, a, f, tc, total;
   bool use_tc;
+  // stored-pattern mode (single pass): per-iteration stores and the phase-2 scratch
+  bool stored;
+  size_t kap, Zs[ICNN_MAX_LAYERS], Ds[ICNN_MAX_LAYERS], As[ICNN_MAX_LAYERS], Zts[ICNN_MAX_LAYERS], Ty[ICNN_MAX_LAYERS];
+  size_t P_hi, P_lo, Pk, Sout;
 };
 
 // tensor-core GEMMs (3xTF32) for the forward / tangent / backward products once a 128-row tile fills;
@@ -194,7 +244,18 @@ static bool gdb_use_tc(const icnn_picnn* h, int B) {
   return h->use_tc && B >= 64 && !(v && v[0] == 's');
 }
 
-static GdbLayout gdb_layout(const icnn_picnn* h, int B) {
+// Single pass with the activation patterns, deltas and pre-gating products of every iteration kept in
+// HBM (then every iteration-independent product is hoisted and the rest is batched over the
+// iterations) when that store fits ICNN_GDB_STORE_GB (default 24) GiB; ICNN_GDB=twopass disables it.
+static bool gdb_want_stored(const icnn_picnn* h, int B, int nIter, size_t store_floats) {
+  const char* v = getenv("ICNN_GDB");
+  if (!gdb_use_tc(h, B) || nIter < 1 || (v && v[0] == 't')) return false;
+  double cap = 24.0;
+  if (const char* c = getenv("ICNN_GDB_STORE_GB")) cap = atof(c);
+  return (double)store_floats * 4.0 <= cap * 1073741824.0;
+}
+
+static GdbLayout gdb_layout(const icnn_picnn* h, int B, int nIter) {
   GdbLayout lo{};
   size_t off = 0;
   auto take = [&](size_t nfl) { size_t o = off; off += (nfl + 63) & ~(size_t)63; return o; };
@@ -211,6 +272,22 @@ static GdbLayout gdb_layout(const icnn_picnn* h, int B) {
   lo.tc = off;
   lo.use_tc = gdb_use_tc(h, B);
   if (lo.use_tc) off += picnn_gdb_tc_ws_floats(h, B, nullptr, nullptr);
+  {
+    const size_t base = off, R = (size_t)(nIter > 0 ? nIter : 1) * B;
+    int spmax = 1;
+    for (int i = 1; i <= h->L; ++i) spmax = h->prev(i) > spmax ? h->prev(i) : spmax;
+    lo.kap = take((size_t)(nIter > 0 ? nIter : 1));
+    for (int i = 0; i < h->L; ++i) {
+      lo.Zs[i] = take(R * h->hidden[i]);
+      lo.Ds[i] = take(R * h->hidden[i]);
+      lo.Ty[i] = take((size_t)B * h->hidden[i]);
+      if (i > 0) { lo.As[i] = take(R * h->prev(i)); lo.Zts[i] = take(R * h->hidden[i]); }
+    }
+    lo.P_hi = take(R * ld4(spmax)); lo.P_lo = take(R * ld4(spmax)); lo.Pk = take(R * spmax);
+    lo.Sout = take((size_t)B * h->hidden[h->L - 1]);
+    lo.stored = gdb_want_stored(h, B, nIter, off - base);
+    if (!lo.stored) off = base;
+  }
   lo.total = off;
   return lo;
 }
@@ -221,12 +298,14 @@ static GdbLayout gdb_layout(const icnn_picnn* h, int B) {
     if (_le != cudaSuccess) { set_error("%s launch: %s", what, cudaGetErrorString(_le)); return ICNN_E_CUDA; } \
   } while (0)
 
-// One GD iteration's primal forward + backward on the FFMA path.  With acc != nullptr also the
-// tangent forward and the gradient accumulations (pass 2).
+// One GD iteration's primal forward + backward.  acc != nullptr: also the tangent forward and the
+// gradient accumulations (pass 2 of the two-pass mode).  store_it >= 0 (stored-pattern mode, tensor-core
+// path only): the primal pass writes Z_l, delta_l and delta_l Wz_l^T of this iteration into the stores
+// and accumulates Delta_l += kappa delta_l.
 struct GdbAcc { const icnn_gd_grads* gr; float kappa; };
 
 static int gdb_iteration(const icnn_picnn* h, const icnn_gates* gt, float* ws, const GdbLayout& lo,
-                         const GdbAcc* acc, cudaStream_t st) {
+                         const GdbAcc* acc, int store_it, float store_kappa, cudaStream_t st) {
   const int B = gt->B, n = h->n, L = h->L;
   float* y = ws + lo.y; float* g = ws + lo.g; float* f = ws + lo.f; float* av = ws + lo.a;
   float* dl[2] = {ws + lo.dl[0], ws + lo.dl[1]};
@@ -234,6 +313,19 @@ static int gdb_iteration(const icnn_picnn* h, const icnn_gates* gt, float* ws, c
   if (lo.use_tc) {
     tb.y = y; tb.g = g; tb.dp[0] = dl[0]; tb.dp[1] = dl[1];
     for (int i = 0; i < L; ++i) { tb.Z[i] = ws + lo.Z[i]; tb.Zt[i] = ws + lo.Zt[i]; tb.Dacc[i] = ws + lo.Dacc[i]; }
+    if (acc) {
+      tb.want_plain = true; tb.acc_delta = true; tb.kappa = acc->kappa;
+      for (int i = 1; i < L; ++i) tb.dcz[i] = acc->gr->dcz[i];
+    }
+    if (store_it >= 0) {
+      tb.want_plain = true; tb.acc_delta = true; tb.kappa = store_kappa;
+      for (int i = 0; i < L; ++i) {
+        const size_t r = (size_t)store_it * B;
+        tb.Z[i] = ws + lo.Zs[i] + r * h->hidden[i];
+        tb.dstore[i] = ws + lo.Ds[i] + r * h->hidden[i];
+        if (i > 0) tb.astore[i] = ws + lo.As[i] + r * h->prev(i);
+      }
+    }
     picnn_gdb_tc_ws_floats(h, B, &tb, ws + lo.tc);
     int rc = picnn_gdb_tc_forward(h, gt, tb, acc != nullptr, st);
     if (rc) return rc;
@@ -251,10 +343,12 @@ static int gdb_iteration(const icnn_picnn* h, const icnn_gates* gt, float* ws, c
       GDB_LAUNCH(launch_gemm<2>(a, st), "gd_backward tangent");
     }
   }
-  out_layer_launch(h, gt, ws + lo.Z[L - 1], y, f, dl[0], lo.use_tc ? tb.dh[0] : nullptr, lo.use_tc ? tb.dl[0] : nullptr,
-                   g, n, nullptr, nullptr, 0, nullptr, st);
   const int sl = h->hidden[L - 1];
   const long long NL = (long long)B * sl;
+  float* dlast = store_it >= 0 ? tb.dstore[L - 1] : dl[0];     // plain delta_{L-1}
+  out_layer_launch(h, gt, lo.use_tc ? tb.Z[L - 1] : ws + lo.Z[L - 1], y, f, dlast, lo.use_tc ? tb.dh[0] : nullptr,
+                   lo.use_tc ? tb.dl[0] : nullptr, g, n, nullptr, nullptr, 0, nullptr, st);
+  if (store_it >= 0) axpy_kernel<<<(unsigned)((NL + 255) / 256), 256, 0, st>>>(ws + lo.Dacc[L - 1], dlast, store_kappa, NL);
   if (acc) {
     const float kp = acc->kappa;
     axpy_kernel<<<(unsigned)((NL + 255) / 256), 256, 0, st>>>(ws + lo.Dacc[L - 1], dl[0], kp, NL);
@@ -274,7 +368,7 @@ static int gdb_iteration(const icnn_picnn* h, const icnn_gates* gt, float* ws, c
       GDB_LAUNCH(launch_wgrad(w, st), "gd_backward wgrad");
     }
     if (lo.use_tc) {
-      int rc = picnn_gdb_tc_backward_layer(h, gt, tb, i, cur, acc ? acc->gr : nullptr, acc ? acc->kappa : 0.f, st);
+      int rc = picnn_gdb_tc_backward_layer(h, gt, tb, i, cur, st);
       if (rc) return rc;
       cur ^= 1;
       continue;
@@ -297,9 +391,9 @@ static int gdb_iteration(const icnn_picnn* h, const icnn_gates* gt, float* ws, c
 
 using namespace icnn;
 
-extern "C" size_t icnn_gd_backward_workspace_bytes(const icnn_picnn_t* h, int32_t B) {
-  if (!h || B <= 0) return 0;
-  return sizeof(float) * gdb_layout(h, B).total;
+extern "C" size_t icnn_gd_backward_workspace_bytes(const icnn_picnn_t* h, int32_t B, int32_t nIter) {
+  if (!h || B <= 0 || nIter < 0) return 0;
+  return sizeof(float) * gdb_layout(h, B, nIter).total;
 }
 
 extern "C" int icnn_gd_backward(const icnn_picnn_t* h, const icnn_gates* gates, const float* y0,
@@ -315,7 +409,7 @@ extern "C" int icnn_gd_backward(const icnn_picnn_t* h, const icnn_gates* gates, 
   for (int l = 0; l <= L; ++l)
     ICNN_REQUIRE(gr->dWy[l] && gr->dcy[l] && (l == 0 || (gr->dWz[l] && gr->dcz[l])), "null gradient buffer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const GdbLayout lo = gdb_layout(h, B);
+  const GdbLayout lo = gdb_layout(h, B, nIter);
   float* ws = static_cast<float*>(workspace);
   const long long N = (long long)B * n;
   const unsigned gN = (unsigned)((N + 255) / 256);
@@ -342,12 +436,63 @@ extern "C" int icnn_gd_backward(const icnn_picnn_t* h, const icnn_gates* gates, 
     if (l < L) ICNN_CUDA_CHECK(cudaMemsetAsync(ws + lo.Dacc[l], 0, sizeof(float) * (size_t)B * sl, st));
   }
 
+  const float* av = ws + lo.a;
+  if (lo.stored) {
+    // ---- single pass: the GD loop with per-iteration stores, then the batched tangent phase ----
+    // (pageable source: the call returns once kappa has been staged, so the vector may go out of scope)
+    ICNN_CUDA_CHECK(cudaMemcpyAsync(ws + lo.kap, kappa.data(), sizeof(float) * nIter, cudaMemcpyHostToDevice, st));
+    ICNN_CUDA_CHECK(cudaMemcpyAsync(ws + lo.y, y0, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+    ICNN_CUDA_CHECK(cudaMemsetAsync(ws + lo.v, 0, sizeof(float) * N, st));
+    for (int it = 0; it < nIter; ++it) {
+      int rc = gdb_iteration(h, gates, ws, lo, nullptr, it, kappa[it], st);
+      if (rc) return rc;
+      gd_update_kernel<<<gN, 256, 0, st>>>(ws + lo.y, ws + lo.v, ws + lo.g, N, lr, momentum);
+    }
+    ICNN_CUDA_CHECK(cudaMemcpyAsync(yN, ws + lo.y, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+    mse_grad_kernel<<<gN, 256, 0, st>>>(ws + lo.a, ws + lo.y, trueY, loss_scale, N);
+    const long long R = (long long)nIter * B;
+    for (int l = 0; l < L; ++l) {   // Ty_l = (a o cy_l) Wy_l: independent of the iteration
+      GemmArgs a{};
+      a.M = B; a.N = h->hidden[l]; a.K0 = 0; a.K1 = n; a.A1 = av; a.G1 = gates->cy[l]; a.lda1 = n;
+      a.a1_scale = 1.f; a.a1_shift = 0.f; a.W = h->Wcat[l] + (size_t)h->prev(l) * h->hidden[l]; a.ldw = a.N;
+      a.Zmask = nullptr; a.Z = ws + lo.Ty[l]; a.alpha = h->alpha;
+      GDB_LAUNCH(launch_gemm<2>(a, st), "gd_backward Ty");
+    }
+    for (int l = 1; l <= L; ++l) {
+      const int sp = h->prev(l);
+      const long long BS = (long long)B * sp;
+      StageArgs sa{};
+      sa.B = B; sa.S = sp; sa.nIter = nIter; sa.alpha = h->alpha; sa.kappa = ws + lo.kap;
+      if (l == 1) { sa.Zs = ws + lo.Zs[0]; sa.Ty = ws + lo.Ty[0]; } else sa.Zt_st = ws + lo.Zts[l - 1];
+      sa.dcz = gr->dcz[l];
+      if (l < L) {
+        sa.As = ws + lo.As[l]; sa.cz = gates->cz[l];
+        sa.P_hi = ws + lo.P_hi; sa.P_lo = ws + lo.P_lo; sa.ldp = ld4(sp); sa.Pk = ws + lo.Pk;
+      } else {
+        sa.wz = h->Wcat[L]; sa.Sout = ws + lo.Sout;
+      }
+      tangent_stage_kernel<<<(unsigned)((BS + 255) / 256), 256, 0, st>>>(sa);
+      WgradArgs w{};
+      if (l < L) {
+        int rc = picnn_gdb_tc_stored_tangent(h, l, R, B, ws + lo.P_hi, ws + lo.P_lo, ws + lo.Ty[l], ws + lo.Zs[l],
+                                             ws + lo.Zts[l], st);
+        if (rc) return rc;
+        // dWz_l = sum_i kappa_i (zt_{l-1}^(i) o cz_l)^T delta_l^(i): one GEMM with K = nIter * B
+        w.M = sp; w.N = h->hidden[l]; w.Kb = (int)R; w.A = ws + lo.Pk; w.G = nullptr; w.lda = sp;
+        w.D = ws + lo.Ds[l]; w.ldd = w.N; w.C = gr->dWz[l]; w.ldc = w.N; w.kappa = 1.f;
+      } else {   // dWz_L[j] = sum_b S[b, j] cz_L[b, j]
+        w.M = sp; w.N = 1; w.Kb = B; w.A = ws + lo.Sout; w.G = gates->cz[L]; w.lda = sp; w.D = nullptr; w.ldd = 1;
+        w.C = gr->dWz[L]; w.ldc = 1; w.kappa = 1.f;
+      }
+      GDB_LAUNCH(launch_wgrad(w, st), "gd_backward wgrad (stored)");
+    }
+  } else
   for (int pass = 0; pass < 2; ++pass) {
     ICNN_CUDA_CHECK(cudaMemcpyAsync(ws + lo.y, y0, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
     ICNN_CUDA_CHECK(cudaMemsetAsync(ws + lo.v, 0, sizeof(float) * N, st));
     for (int it = 0; it < nIter; ++it) {
       GdbAcc acc{gr, kappa[it]};
-      int rc = gdb_iteration(h, gates, ws, lo, pass ? &acc : nullptr, st);
+      int rc = gdb_iteration(h, gates, ws, lo, pass ? &acc : nullptr, -1, 0.f, st);
       if (rc) return rc;
       gd_update_kernel<<<gN, 256, 0, st>>>(ws + lo.y, ws + lo.v, ws + lo.g, N, lr, momentum);
     }
@@ -363,7 +508,6 @@ extern "C" int icnn_gd_backward(const icnn_picnn_t* h, const icnn_gates* gates, 
   }
 
   // y-gate terms from the accumulated Delta_l
-  const float* av = ws + lo.a;
   for (int l = 0; l < L && nIter > 0; ++l) {
     WgradArgs w{};
     w.M = n; w.N = h->hidden[l]; w.Kb = B; w.A = av; w.G = gates->cy[l]; w.lda = n;

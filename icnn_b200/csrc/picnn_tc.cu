@@ -149,7 +149,10 @@ struct TcArgs {
   // GD training backward (GDB instantiation only, gd_backward.cu):
   //   mode 0 with tangent != 0: Z = act'(D) o acc (D holds the primal activation), no bias
   //   mode 1: optional plain copy of delta_prev, dCz += kappa * Ztprev o acc, Dacc += kappa * delta_prev
+  //   mode 0 with tangent == 2 (stored-pattern phase): Z = act'(Zmask) o (acc + D[(row % drow_mod), :])
+  //   mode 1: optional plain copy of the pre-gating product acc (acc_plain, [M, N0])
   int tangent; float* dprev_plain; float* dCz; const float* Ztprev; float* Dacc; float kappa;
+  const float* Zmask; int drow_mod; float* acc_plain;
   // mode 3 (x-path gate GEMM): out = acc + bias[col]; up to 4 column ranges [rbeg[r], rbeg[r+1]) each with
   // its own ReLU flag and destination (row pitch rld[r]); range 0 may instead be written as a TF32
   // hi/lo pair (the next u-layer operand)
@@ -307,10 +310,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           for (int qq = 0; qq < S; ++qq) acc += *cl.map_shared_rank(P + rr * PP + c, qq);
           if (a.mode == 0) {
             const long long idx = (long long)m * a.N + nn;
-            const float dv = __ldg(a.D + idx);
+            float dv;
+            if (GDB && a.tangent == 2) dv = __ldg(a.D + (long long)(m % a.drow_mod) * a.N + nn);
+            else dv = __ldg(a.D + idx);
             const float x = acc + dv;
             float z = x > 0.f ? x : a.alpha * x;
-            if constexpr (GDB) { if (a.tangent) z = (dv > 0.f ? 1.f : a.alpha) * acc; }
+            if constexpr (GDB) {
+              if (a.tangent == 1) z = (dv > 0.f ? 1.f : a.alpha) * acc;
+              else if (a.tangent == 2) z = (__ldg(a.Zmask + idx) > 0.f ? 1.f : a.alpha) * x;
+            }
             a.Z[idx] = z;
             if (a.nxt_hi) {
               const float p = z * __ldg(a.Cz_next + idx);
@@ -328,10 +336,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               a.dprev_lo[(long long)m * a.dprev_ld + nn] = tf32_lo(p, h);
               if constexpr (GDB) {
                 if (a.dprev_plain) a.dprev_plain[idx] = p;
-                if (a.dCz) {
-                  a.dCz[idx] = fmaf(a.kappa * __ldg(a.Ztprev + idx), acc, a.dCz[idx]);
-                  a.Dacc[idx] = fmaf(a.kappa, p, a.Dacc[idx]);
-                }
+                if (a.acc_plain) a.acc_plain[idx] = acc;
+                if (a.dCz) a.dCz[idx] = fmaf(a.kappa * __ldg(a.Ztprev + idx), acc, a.dCz[idx]);
+                if (a.Dacc) a.Dacc[idx] = fmaf(a.kappa, p, a.Dacc[idx]);
               }
             } else {
               const int e = nn - a.N0;
@@ -380,8 +387,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           if (nv && m < a.M) {
             if (a.mode == 0) {
               const long long idx = (long long)m * a.N + nn;
-              in0[i] = __ldg(a.D + idx);
-              if (a.nxt_hi) in1[i] = __ldg(a.Cz_next + idx);
+              if (GDB && a.tangent == 2) {
+                in0[i] = __ldg(a.D + (long long)(m % a.drow_mod) * a.N + nn);
+                in1[i] = __ldg(a.Zmask + idx);
+              } else {
+                in0[i] = __ldg(a.D + idx);
+                if (a.nxt_hi) in1[i] = __ldg(a.Cz_next + idx);
+              }
             } else if (a.mode == 3) {
               in0[i] = __ldg(a.bias + nn);
             } else if (a.mode == 1) {
@@ -390,7 +402,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 in0[i] = __ldg(a.Zprev + idx);
                 in1[i] = __ldg(a.Cz + idx);
                 if constexpr (GDB) {
-                  if (a.dCz) { in2[i] = __ldg(a.Ztprev + idx); in3[i] = a.dCz[idx]; in4[i] = a.Dacc[idx]; }
+                  if (a.dCz) { in2[i] = __ldg(a.Ztprev + idx); in3[i] = a.dCz[idx]; }
+                  if (a.Dacc) in4[i] = a.Dacc[idx];
                 }
               } else {
                 const int e = nn - a.N0;
@@ -408,7 +421,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             const long long idx = (long long)m * a.N + nn;
             const float x = acc[i] + in0[i];
             float z = x > 0.f ? x : a.alpha * x;
-            if constexpr (GDB) { if (a.tangent) z = (in0[i] > 0.f ? 1.f : a.alpha) * acc[i]; }
+            if constexpr (GDB) {
+              if (a.tangent == 1) z = (in0[i] > 0.f ? 1.f : a.alpha) * acc[i];
+              else if (a.tangent == 2) z = (in1[i] > 0.f ? 1.f : a.alpha) * x;
+            }
             a.Z[idx] = z;
             if (a.nxt_hi) {
               const float p = z * in1[i];
@@ -426,10 +442,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               if constexpr (GDB) {
                 const long long idx = (long long)m * a.N0 + nn;
                 if (a.dprev_plain) a.dprev_plain[idx] = p;
-                if (a.dCz) {
-                  a.dCz[idx] = fmaf(a.kappa * in2[i], acc[i], in3[i]);
-                  a.Dacc[idx] = fmaf(a.kappa, p, in4[i]);
-                }
+                if (a.acc_plain) a.acc_plain[idx] = acc[i];
+                if (a.dCz) a.dCz[idx] = fmaf(a.kappa * in2[i], acc[i], in3[i]);
+                if (a.Dacc) a.Dacc[idx] = fmaf(a.kappa, p, in4[i]);
               }
             } else {
               const int e = nn - a.N0;
@@ -775,19 +790,34 @@ int picnn_gdb_tc_forward(const icnn_picnn* h, const icnn_gates* gt, const GdbTcB
   return ICNN_OK;
 }
 
-// backward GEMM of hidden layer i: delta_i (hi/lo in slot cur) -> delta_{i-1} (slot cur^1: hi/lo + plain) and g;
-// with gr, dcz_i += kappa zt_{i-1} o (delta_i Wz_i^T) and Delta_{i-1} += kappa delta_{i-1} in the epilogue
+// backward GEMM of hidden layer i: delta_i (hi/lo in slot cur) -> delta_{i-1} (slot cur^1: hi/lo, optionally
+// plain) and g; the optional accumulations / plain stores of GdbTcBufs run in the epilogue
 int picnn_gdb_tc_backward_layer(const icnn_picnn* h, const icnn_gates* gt, const GdbTcBufs& b, int i, int cur,
-                                const icnn_gd_grads* gr, float kappa, cudaStream_t st) {
+                                cudaStream_t st) {
   TcArgs a{};
   a.M = gt->B; a.N0 = h->prev(i); a.N = a.N0 + h->n; a.K = h->hidden[i]; a.mode = 1; a.alpha = h->alpha;
   a.Zprev = i ? b.Z[i - 1] : nullptr; a.Cz = i ? gt->cz[i] : nullptr;
   a.dprev_hi = b.dh[cur ^ 1]; a.dprev_lo = b.dl[cur ^ 1]; a.dprev_ld = ld4(a.N0);
   a.Cy = gt->cy[i]; a.g = b.g; a.g_row_stride = h->n; a.n = h->n; a.g_scale = 1.f;
-  if (gr && i > 0) {
-    a.dprev_plain = b.dp[cur ^ 1]; a.dCz = gr->dcz[i]; a.Ztprev = b.Zt[i - 1]; a.Dacc = b.Dacc[i - 1]; a.kappa = kappa;
+  if (i > 0) {
+    if (b.want_plain) a.dprev_plain = b.dstore[i - 1] ? b.dstore[i - 1] : b.dp[cur ^ 1];
+    a.acc_plain = b.astore[i];
+    if (b.dcz[i]) { a.dCz = b.dcz[i]; a.Ztprev = b.Zt[i - 1]; }
+    if (b.acc_delta) a.Dacc = b.Dacc[i - 1];
+    a.kappa = b.kappa;
   }
   return launch_tc_gemm(b.dh[cur], b.dl[cur], ld4(a.K), h->Wb_hi[i], h->Wb_lo[i], ld4(a.K), a, st, true);
+}
+
+// stored-pattern phase, hidden layer l >= 1, all nIter iterations in one GEMM (M = nIter * B rows):
+//   Zt[r, :] = act'(Zs[r, :]) o (P[r, :] Wz_l + Ty[r % B, :]),   P = zt_{l-1} o cz_l (TF32 hi/lo, pitch ld4)
+int picnn_gdb_tc_stored_tangent(const icnn_picnn* h, int l, long long M, int B, const float* P_hi, const float* P_lo,
+                                const float* Ty, const float* Zs, float* Zt, cudaStream_t st) {
+  TcArgs a{};
+  a.M = (int)M; a.N = h->hidden[l]; a.K = h->prev(l); a.mode = 0; a.tangent = 2; a.alpha = h->alpha;
+  a.D = Ty; a.drow_mod = B; a.Zmask = Zs; a.Z = Zt;
+  // Wf_l is [s_l, s_{l-1} + n] K-major: its first s_{l-1} columns are Wz_l^T
+  return launch_tc_gemm(P_hi, P_lo, ld4(a.K), h->Wf_hi[l], h->Wf_lo[l], ld4(h->prev(l) + h->n), a, st, true);
 }
 
 // ---- x-path (gate precompute) -------------------------------------------

@@ -57,7 +57,7 @@ def gd_grad(fg: BoundPICNN, y0, trueY, nIter=30, lr=0.01, momentum=0.3, loss_sca
         yN = z(B, n)
         arrs = [_capi.ptr_array(v) for v in (dWy, dWz, dcy, dcz)]
         gr = _capi.GdGrads(*[C.cast(a, _capi._fpp) for a in arrs])
-        ws = torch.empty(max(_capi.lib.icnn_gd_backward_workspace_bytes(net._h, B), 4), dtype=torch.uint8,
+        ws = torch.empty(max(_capi.lib.icnn_gd_backward_workspace_bytes(net._h, B, int(nIter)), 4), dtype=torch.uint8,
                          device=dev)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         _capi.check(_capi.lib.icnn_gd_backward(net._h, C.byref(fg.c_gates), y0d.data_ptr(), tY.data_ptr(),

@@ -186,14 +186,16 @@ int icnn_gd_solve(const icnn_picnn_t* h, const icnn_gates* gates, float* y32, fl
  *   dWy[l] [n, s_l], dWz[l] [s_{l-1}, s_l], dcy[l] [B, n], dcz[l] [B, s_{l-1}]   (l = 0..L; [0] of
  *   dWz/dcz unused; the additive gate d_l gets no gradient).  All buffers device f32, overwritten.
  * The x-path parameters follow from (dcy, dcz) by ordinary dense-layer backprop on the caller's side.
- * FP32 FFMA path; the affine RL wrapper is not supported here (ICNN_E_UNSUPPORTED). */
+ * workspace = icnn_gd_backward_workspace_bytes(h, B, nIter) device bytes (it includes, when it fits
+ * ICNN_GDB_STORE_GB, the per-iteration stores of the single-pass mode).  The affine RL wrapper is not
+ * supported here (ICNN_E_UNSUPPORTED). */
 typedef struct {
   float* const* dWy;
   float* const* dWz;
   float* const* dcy;
   float* const* dcz;
 } icnn_gd_grads;
-size_t icnn_gd_backward_workspace_bytes(const icnn_picnn_t* h, int32_t B);
+size_t icnn_gd_backward_workspace_bytes(const icnn_picnn_t* h, int32_t B, int32_t nIter);
 int icnn_gd_backward(const icnn_picnn_t* h, const icnn_gates* gates, const float* y0, const float* trueY,
                      float loss_scale, int32_t nIter, float lr, float momentum, float* yN,
                      const icnn_gd_grads* grads, void* workspace, void* stream);

@@ -95,7 +95,7 @@ int main(void) {
     CK(cudaMalloc((void**)&dcz1, B * S * 4));
     float* dWy[2] = {dWy0, dWy1}; float* dWz[2] = {NULL, dWz1}; float* dcy[2] = {dcy0, dcy1}; float* dcz[2] = {NULL, dcz1};
     icnn_gd_grads gr = {dWy, dWz, dcy, dcz};
-    void* ws2; CK(cudaMalloc(&ws2, icnn_gd_backward_workspace_bytes(h, B) + 256));
+    void* ws2; CK(cudaMalloc(&ws2, icnn_gd_backward_workspace_bytes(h, B, 1) + 256));
     RC(icnn_gd_backward(h, &gates, yd, tYd, scale, 1, lr, mom, yNd, &gr, ws2, NULL));
     CK(cudaDeviceSynchronize());
     float y1[B * N], gw[N];

@@ -40,7 +40,7 @@ def test_bad_arguments_are_rejected_without_touching_the_gpu():
     cfg = _capi.BundleCfg()
     assert _capi.lib.icnn_bundle_step(C.byref(cfg), C.byref(bufs), 0, None) == -1
     assert _capi.lib.icnn_gd_backward(None, None, None, None, 1.0, 3, 0.01, 0.3, None, None, None, None) == -1
-    assert _capi.lib.icnn_gd_backward_workspace_bytes(None, 4) == 0
+    assert _capi.lib.icnn_gd_backward_workspace_bytes(None, 4, 3) == 0
     with pytest.raises(_capi.IcnnError):
         _capi.check(-1)
 

@@ -121,6 +121,26 @@ def test_ffma_and_tensor_core_paths_agree(monkeypatch):
                 assert relerr(a, b.astype(np.float64)) < 5e-5, k
 
 
+def test_single_pass_and_two_pass_modes_agree(monkeypatch):
+    """Default on the tensor-core path: ONE pass over the GD loop with every iteration's activation
+    patterns / deltas kept in HBM and the tangent work batched over the iterations; ICNN_GDB=twopass
+    replays the loop instead (the mode used when the stores exceed ICNN_GDB_STORE_GB)."""
+    import icnn_b200
+    for dims, B, nIter in (((40, 64, [96, 80]), 256, 5), ((20, 37, [50, 21, 33]), 100, 7), ((16, 24, [40]), 64, 3)):
+        p, x, y0, tY = _dims_case(*dims, B, seed=5)
+        fg = icnn_b200.PICNN.from_params(p).bind(x)
+        monkeypatch.delenv("ICNN_GDB", raising=False)
+        y_a, g_a = icnn_b200.gd_grad.gd_grad(fg, y0, tY, nIter=nIter, lr=0.02, momentum=0.5)
+        monkeypatch.setenv("ICNN_GDB", "twopass")
+        y_b, g_b = icnn_b200.gd_grad.gd_grad(fg, y0, tY, nIter=nIter, lr=0.02, momentum=0.5)
+        monkeypatch.delenv("ICNN_GDB")
+        np.testing.assert_array_equal(y_a, y_b)          # the same primal kernels in both modes
+        for k in ("Wy", "Wz", "dcy", "dcz"):
+            for a, b in zip(g_a[k], g_b[k]):
+                if a is not None:
+                    assert relerr(a, b.astype(np.float64)) < 2e-5, (dims, k)
+
+
 def test_yn_is_the_gd_solve_iterate():
     import icnn_b200
     p, x, y0 = synth.make_inputs("C3", B=128)
