@@ -16,14 +16,18 @@
 //   dWz_l = sum_i kappa_i (zt_{l-1}^(i) o cz_l)^T delta_l^(i)
 //   dcz_l = sum_i kappa_i zt_{l-1}^(i) o (delta_l^(i) Wz_l^T)
 //
-// Pass 1 runs the GD loop to y_N (deterministic kernels), a = loss_scale (y_N - trueY); pass 2 replays
-// the same loop (bit-identical iterates) with, per iteration: primal forward, tangent forward (the same
-// gated product with the activation pattern of the primal Z_l), backward with the dcz / Delta
-// accumulation fused into its epilogue, and one weight-gradient GEMM per Wz_l (reduction over the
-// batch, split over a thread-block cluster and reduced through distributed shared memory -- no
-// atomics, deterministic).  The three gated products run on the tcgen05 3xTF32 kernel
-// (picnn_tc.cu, GDB instantiation) once the batch fills a 128-row tile, else on the FP32 FFMA
-// kernel (gated_gemm.cuh, MODE 0 / 2 / 1); the weight-gradient GEMM is FP32 FFMA in both cases.
+// Single-pass mode (tensor-core path, stores within ICNN_GDB_STORE_GB): the GD loop runs once; the
+// GDB epilogues of tc_gemm_kernel keep Z_l^(i), delta_l^(i) and delta_l^(i) Wz_l^T of every iteration
+// in HBM and accumulate Delta_l (kappa does not depend on a).  With a known, Ty_l = (a o cy_l) Wy_l is
+// iteration-independent, zt_0^(i) = act'(Z_0^(i)) o Ty_0 is elementwise, and per hidden layer ONE
+// tcgen05 GEMM over all iterations (M = nIter*B) gives zt_l, ONE weight-gradient GEMM (K = nIter*B)
+// gives dWz_l, and tangent_stage_kernel reduces dcz_l over the iterations.
+// Two-pass mode (fallback; also the FP32 FFMA path for B < 64): pass 1 -> y_N, pass 2 replays the
+// deterministic loop (bit-identical iterates) with, per iteration, the tangent forward (the same
+// gated product with the activation pattern of the primal Z_l), the dcz / Delta accumulation fused
+// into the backward epilogue, and one weight-gradient GEMM per Wz_l.
+// wgrad_gemm_kernel: FP32 FFMA, reduction over the batch split over a thread-block cluster and
+// summed through distributed shared memory -- no atomics, deterministic.
 #include "gated_gemm.cuh"
 
 #include <cstdlib>
