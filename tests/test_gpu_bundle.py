@@ -370,3 +370,33 @@ def test_single_sample_solve_alias():
     o = bundle_np.solve_batch(fgb, y0.copy(), nIter=6, variant="dual")
     assert xs.shape == (159,) and seen == list(range(len(seen))) and len(seen) >= 1
     assert np.abs(xs - o[0][0]).max() < 1e-5
+
+
+def test_callback_mode_with_a_conv_picnn_fg():
+    """the reference's Olivetti energy is CONVOLUTIONAL
+    (completion/icnn_ebundle.py:337-452); the fused path covers fully-connected PICNNs, and any other
+    architecture goes through callback mode -- fg is the user's own callable (here a torch conv-PICNN on
+    the GPU, float32 like the TF fetch), the per-sample bundle work runs in K2.  Checked against the
+    float64 oracle driven by the same network evaluated in float64 on the CPU, at the Olivetti dims
+    (y = the 64 x 32 left half, n_y = 2048)."""
+    import torch
+    from conv_picnn import ConvPICNN
+    from icnn_b200 import bundle_entropy as be
+    B, H, W, nIter = 8, 64, 32, 6
+    net64 = ConvPICNN(H, W, seed=1, dtype=torch.float64)
+    rs = np.random.RandomState(0)
+    x = rs.uniform(size=(B, H * W))
+    y0 = np.full((B, H * W), 0.5)
+    yo, Go, _, lo, _, _ = bundle_np.solve_batch(net64.make_fg(x), y0.copy(), nIter=nIter)
+    net32 = net64.to(torch.float32, "cuda")
+    trace = []
+    for as_numpy in (True, False):          # numpy (f, g) like the reference, or CUDA tensors (no host hop for g)
+        y, G, h, lam, ys, nIters = be.solveBatch(net32.make_fg(x, as_numpy=as_numpy), y0.copy(), nIter=nIter,
+                                                 callback=lambda t, fi, xi: trace.append((t, float(np.mean(fi)))))
+        d = np.abs(y - yo).max(axis=1)
+        print("conv-PICNN callback mode: max %.2e median %.2e" % (d.max(), np.median(d)), [len(g) for g in G])
+        assert np.median(d) < 1e-4 and np.mean(d < 1e-4) >= 0.75, d
+        assert [len(g) for g in G] == [len(g) for g in Go]
+        for u in range(B):
+            assert abs(lam[u].sum() - 1) < 1e-6
+    assert [t for t, _ in trace[:nIter]] == list(range(nIter))
