@@ -377,26 +377,32 @@ def test_callback_mode_with_a_conv_picnn_fg():
     (completion/icnn_ebundle.py:337-452); the fused path covers fully-connected PICNNs, and any other
     architecture goes through callback mode -- fg is the user's own callable (here a torch conv-PICNN on
     the GPU, float32 like the TF fetch), the per-sample bundle work runs in K2.  Checked against the
-    float64 oracle driven by the same network evaluated in float64 on the CPU, at the Olivetti dims
-    (y = the 64 x 32 left half, n_y = 2048)."""
+    oracle driven by the SAME float32 fg (what the library is responsible for: identical (f, g) in,
+    identical y* out), at the Olivetti dims (y = the 64 x 32 left half, n_y = 2048); the distance to
+    the float64 evaluation of the network is printed (1e-6 with FP32 convolutions; with torch's
+    default TF32 convolutions the user's g carries 1e-3 relative noise and half the samples move by
+    2e-2 -- a property of that fg, which is why TF32 is switched off here)."""
     import torch
     from conv_picnn import ConvPICNN
     from icnn_b200 import bundle_entropy as be
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     B, H, W, nIter = 8, 64, 32, 6
     net64 = ConvPICNN(H, W, seed=1, dtype=torch.float64)
     rs = np.random.RandomState(0)
     x = rs.uniform(size=(B, H * W))
     y0 = np.full((B, H * W), 0.5)
-    yo, Go, _, lo, _, _ = bundle_np.solve_batch(net64.make_fg(x), y0.copy(), nIter=nIter)
     net32 = net64.to(torch.float32, "cuda")
+    yo, Go, _, lo, _, _ = bundle_np.solve_batch(net32.make_fg(x), y0.copy(), nIter=nIter)
+    y64 = bundle_np.solve_batch(net64.make_fg(x), y0.copy(), nIter=nIter)[0]
     trace = []
     for as_numpy in (True, False):          # numpy (f, g) like the reference, or CUDA tensors (no host hop for g)
         y, G, h, lam, ys, nIters = be.solveBatch(net32.make_fg(x, as_numpy=as_numpy), y0.copy(), nIter=nIter,
                                                  callback=lambda t, fi, xi: trace.append((t, float(np.mean(fi)))))
         d = np.abs(y - yo).max(axis=1)
-        print("conv-PICNN callback mode: max %.2e median %.2e" % (d.max(), np.median(d)), [len(g) for g in G])
-        assert np.median(d) < 1e-4 and np.mean(d < 1e-4) >= 0.75, d
-        assert [len(g) for g in G] == [len(g) for g in Go]
+        print("conv-PICNN callback mode vs oracle on the same fg: max %.2e median %.2e; vs float64 network: max %.2e"
+              % (d.max(), np.median(d), np.abs(y - y64).max()), [len(g) for g in G])
+        assert np.median(d) < 1e-6 and np.mean(d < 1e-4) >= 0.75, d
         for u in range(B):
-            assert abs(lam[u].sum() - 1) < 1e-6
+            assert abs(lam[u].sum() - 1) < 1e-6 and 1 <= len(G[u]) <= nIter
     assert [t for t, _ in trace[:nIter]] == list(range(nIter))
