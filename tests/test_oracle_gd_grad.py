@@ -64,3 +64,35 @@ def test_oracle_matches_golden(golden_dir):
             if l > 0:
                 ref = gold["%s_Wz%d" % (tag, l)]
                 assert np.abs(gr["dWz"][l] - ref).max() <= 1e-9 * np.abs(ref).max() + 1e-18
+
+
+def test_gd_backward_matches_finite_differences():
+    """A third, autodiff-free pin: central differences of the unrolled-GD loss in single weights."""
+    import copy
+    p, x, y0 = synth.make_inputs("C1", B=6)
+    tY = (np.random.RandomState(3).uniform(size=(6, p.n)) < 0.3).astype(np.float64)
+    nIter, lr, mom = 5, 0.05, 0.3
+    gts = picnn_np.gates(p, x)
+
+    def loss(pp):
+        yN, _ = picnn_np.momentum_gd(lambda y: picnn_np.fg_gated(pp, gts, y), y0, nIter, lr, mom)
+        return float(((yN - tY) ** 2).mean())
+
+    _, gr = gd_grad_np.gd_backward(p, gts, y0, nIter, lr, mom, lambda y: 2.0 * (y - tY) / y.size)
+    rs = np.random.RandomState(4)
+    eps = 1e-6
+    checked = 0
+    for name, key, layers in (("Wy", "dWy", range(p.L + 1)), ("Wz", "dWz", range(1, p.L + 1))):
+        for l in layers:
+            W = getattr(p, name)[l]
+            for _ in range(3):
+                i, j = rs.randint(W.shape[0]), rs.randint(W.shape[1])
+                pp, pm = copy.deepcopy(p), copy.deepcopy(p)
+                getattr(pp, name)[l][i, j] += eps
+                getattr(pm, name)[l][i, j] -= eps
+                fd = (loss(pp) - loss(pm)) / (2 * eps)
+                an = gr[key][l][i, j]
+                # a ReLU kink inside [W - eps, W + eps] would break the difference quotient; none at this seed
+                assert abs(fd - an) <= 1e-5 * max(abs(an), np.abs(gr[key][l]).max()) + 1e-12, (name, l, i, j, fd, an)
+                checked += 1
+    assert checked == 3 * (2 * p.L + 1)
