@@ -96,3 +96,25 @@ def test_gd_backward_matches_finite_differences():
                 assert abs(fd - an) <= 1e-5 * max(abs(an), np.abs(gr[key][l]).max()) + 1e-12, (name, l, i, j, fd, an)
                 checked += 1
     assert checked == 3 * (2 * p.L + 1)
+
+
+def test_host_xpath_backward_matches_oracle():
+    """icnn_b200.gd_grad._xpath_backward (the host-side dense backprop of the gate adjoints into the
+    x-path parameters; device-agnostic torch ops) against oracle/gd_grad_np.xpath_backward, on CPU."""
+    import types
+    import torch
+    from icnn_b200.gd_grad import _xpath_backward
+    p, x, y0 = synth.make_inputs("C1", B=9)
+    rs = np.random.RandomState(8)
+    dcy = [rs.randn(9, p.n) for _ in range(p.L + 1)]
+    dcz = [None] + [rs.randn(9, p.hidden[l - 1]) for l in range(1, p.L + 1)]
+    want = gd_grad_np.xpath_backward(p, x, dcy, dcz)
+    t = lambda a: None if a is None else torch.tensor(np.asarray(a), dtype=torch.float64)  # noqa: E731
+    net = types.SimpleNamespace(L=p.L, **{k: [t(a) for a in getattr(p, k)] for k in ("Wu", "bu", "Wzu", "bzu", "Wyu", "byu")})
+    got = _xpath_backward(net, t(x), [t(a) for a in dcy], [t(a) for a in dcz])
+    for k in ("Wu", "bu", "Wzu", "bzu", "Wyu", "byu"):
+        for a, b in zip(got[k], want["d" + k]):
+            if b is None:
+                assert a is None
+            else:
+                np.testing.assert_allclose(a.numpy(), b, rtol=1e-11, atol=1e-13)
