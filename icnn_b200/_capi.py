@@ -13,7 +13,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libicnn_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
+NSTAT = 8
 
 # status / enum mirrors of include/icnn_b200.h
 ST_RUNNING, ST_RANK_STOP, ST_SOLVE_FAIL, ST_NONFINITE, ST_CONVERGED = 0, 2, 3, 4, 5
@@ -24,7 +25,7 @@ SOLVER_PC, SOLVER_NEWTON = 0, 1
 SYMBOLS = [
     "icnn_last_error", "icnn_abi_version", "icnn_device_count",
     "icnn_picnn_create", "icnn_picnn_destroy", "icnn_picnn_workspace_bytes", "icnn_picnn_fg",
-    "icnn_bundle_init", "icnn_bundle_put_fg", "icnn_bundle_step",
+    "icnn_bundle_init", "icnn_bundle_put_fg", "icnn_bundle_put_fg_f64", "icnn_bundle_step",
     "icnn_solve_batch_fused", "icnn_gd_solve", "icnn_tc_gemm_selftest", "icnn_argmin_grad",
     "icnn_picnn_set_xpath", "icnn_picnn_gates_workspace_bytes", "icnn_picnn_gates",
     "icnn_adam_workspace_bytes", "icnn_adam_solve",
@@ -50,7 +51,8 @@ class BundleBufs(C.Structure):
                 ("ys", C.c_void_p), ("h", C.c_void_p), ("lam", C.c_void_p), ("rsum", C.c_void_p),
                 ("gram", C.c_void_p), ("perm", C.c_void_p), ("count", C.c_void_p),
                 ("status", C.c_void_p), ("finished", C.c_void_p), ("nIters", C.c_void_p),
-                ("nactive", C.c_void_p), ("newton_its", C.c_void_p), ("ksum", C.c_void_p)]
+                ("nactive", C.c_void_p), ("newton_its", C.c_void_p), ("ksum", C.c_void_p),
+                ("f64", C.c_void_p), ("iter_stats", C.c_void_p)]
 
 
 class BundleCfg(C.Structure):
@@ -85,6 +87,7 @@ def _load():
                                   C.c_void_p, C.c_void_p]
     lib.icnn_bundle_init.argtypes = [C.POINTER(BundleBufs), C.c_int32, C.c_void_p]
     lib.icnn_bundle_put_fg.argtypes = [C.POINTER(BundleBufs), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.icnn_bundle_put_fg_f64.argtypes = [C.POINTER(BundleBufs), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.icnn_bundle_step.argtypes = [C.POINTER(BundleCfg), C.POINTER(BundleBufs), C.c_int32, C.c_void_p]
     lib.icnn_solve_batch_fused.argtypes = [C.c_void_p, C.POINTER(Gates), C.POINTER(BundleCfg),
                                            C.POINTER(BundleBufs), C.c_void_p, C.c_void_p]

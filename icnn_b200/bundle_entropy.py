@@ -68,8 +68,9 @@ class _Rows:
 class BundleState:
     """Device buffers of one solveBatch call (icnn_bundle_bufs in include/icnn_b200.h)."""
 
-    def __init__(self, B, n, KS, device, keep_xs=True, nIter=10):
+    def __init__(self, B, n, KS, device, keep_xs=True, nIter=10, stats=False, keep_f64=False):
         self.B, self.n, self.KS, self.device = int(B), int(n), int(KS), device
+        self.nIter, self.keep_xs = int(nIter), bool(keep_xs)
         f32, f64, i32 = torch.float32, torch.float64, torch.int32
         e = lambda *shape, dtype: torch.empty(*shape, dtype=dtype, device=device)  # noqa: E731
         self.y = e(B, n, dtype=f64)
@@ -89,12 +90,54 @@ class BundleState:
         self.nactive = e(nIter + 1, dtype=i32)
         self.newton_its = e(B, dtype=i32)
         self.ksum = e(B, dtype=i32)
+        # optional: float64 f of a float64 callback fg; per-iteration statistics (include/icnn_b200.h)
+        self.f64 = e(B, dtype=f64) if keep_f64 else None
+        self.iter_stats = torch.zeros(nIter, _capi.NSTAT, dtype=torch.float64, device=device) if stats else None
         p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         self.c = _capi.BundleBufs(self.B, self.n, self.KS, p(self.y), p(self.y32), p(self.f), p(self.G),
                                   p(self.ys), p(self.h), p(self.lam), p(self.rsum), p(self.gram),
                                   p(self.perm), p(self.count), p(self.status), p(self.finished),
-                                  p(self.nIters), p(self.nactive), p(self.newton_its), p(self.ksum))
+                                  p(self.nIters), p(self.nactive), p(self.newton_its), p(self.ksum),
+                                  p(self.f64), p(self.iter_stats))
         self._host = None
+        self._pin_y = None
+
+    def compatible(self, B, n, KS, device, keep_xs, nIter, stats, keep_f64):
+        """True if this state can be reused (``solveBatch(..., state=st)``) for a problem of that shape."""
+        return (self.B == B and self.n == n and self.KS == KS and self.device == device
+                and self.nIter >= nIter and (self.ys is not None) == bool(keep_xs)
+                and (self.iter_stats is not None or not stats) and (self.f64 is not None or not keep_f64))
+
+    def reset_views(self):
+        self._host = None
+
+    def stats(self):
+        """Per-outer-iteration statistics as a dict of numpy arrays [nIter] (None if not requested):
+        what the reference prints per iteration / what ebundle-vs-gd.py:94-99 plots (mean f - H)."""
+        if self.iter_stats is None:
+            return None
+        a = self.iter_stats.cpu().numpy()
+        ent = np.maximum(a[:, 0], 1.0)
+        return dict(entering=a[:, 0], sum_k=a[:, 1], inner_its=a[:, 2], sum_its_k2=a[:, 3], sum_its_k=a[:, 4],
+                    stopped=a[:, 5], mean_f_minus_H=a[:, 6] / ent)
+
+    def y_host(self, out=None):
+        """y* on the host.  ``out``: a float64 CPU tensor / array to fill in place (pinned memory makes
+        the copy asynchronous-capable and ~4x faster than pageable); else a pinned staging buffer owned
+        by this state is used and a numpy copy is returned."""
+        if out is not None and isinstance(out, torch.Tensor) and out.dtype == torch.float64 and not out.is_cuda \
+                and out.is_contiguous():
+            out.copy_(self.y, non_blocking=out.is_pinned())
+            torch.cuda.current_stream().synchronize()
+            return out.numpy()
+        if self._pin_y is None:
+            try:
+                self._pin_y = torch.empty(self.B, self.n, dtype=torch.float64, pin_memory=True)
+            except RuntimeError:
+                self._pin_y = torch.empty(self.B, self.n, dtype=torch.float64)
+        self._pin_y.copy_(self.y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._pin_y.numpy().copy()
 
     # ---- ragged outputs ---------------------------------------------------------------------
     def _host_small(self):
@@ -119,6 +162,20 @@ class BundleState:
         idx = torch.as_tensor(slots.astype(np.int64), device=self.device)
         rows = src[u].index_select(0, idx).cpu().numpy()
         return [rows[j] for j in range(k)]
+
+
+class _EmptyState:
+    """State of a zero-row call (an empty shard of a sample-sharded batch, icnn_b200/dist.py)."""
+
+    def __init__(self, n, KS, device):
+        self.B, self.n, self.KS, self.device = 0, int(n), int(KS), device
+        self.y = torch.empty(0, n, dtype=torch.float64, device=device)
+        self.nactive = torch.zeros(1, dtype=torch.int32, device=device)
+        self.ys = self.iter_stats = self.f64 = None
+        self.status_host = np.zeros(0, dtype=np.int32)
+
+    def stats(self):
+        return None
 
 
 def _make_cfg(variant, solver, nIter, line_search, rank_tol, max_inner, n, KS):
@@ -155,8 +212,13 @@ def _to_numpy(a):
     return np.asarray(a)
 
 
+def _nvtx(name):
+    return torch.cuda.nvtx.range(name)
+
+
 def solveBatch(fg, initXs, nIter=None, callback=None, solver="pc", *, variant="lib", line_search=None,
-               rank_tol=None, max_inner=0, keep_xs=True, device=None, strict=False, return_state=False):
+               rank_tol=None, max_inner=0, keep_xs=True, device=None, strict=False, return_state=False,
+               state=None, stats=False):
     """argmin_y f(x, y) - H(y) over [0,1]^n by the bundle-entropy method, on the GPU.
 
     Positional/keyword arguments are the reference's; keyword-only extras select which of the
@@ -164,8 +226,12 @@ def solveBatch(fg, initXs, nIter=None, callback=None, solver="pc", *, variant="l
     ``solver``: 'pc' (Mehrotra predictor-corrector, the reference default), 'boyd' (accepted,
     mapped to the same optimum) or 'newton' (converged dual projected Newton).
     Returns ``(x, A, b, lam, xs, nIters)``; A/b/xs are lazy list-of-lists views, lam a lazy list
-    of arrays.  ``initXs`` (numpy) is overwritten with the result like the reference does
-    (lib/bundle_entropy.py:200,228).
+    of arrays.  ``initXs`` (numpy float64, or a float64 CPU torch tensor) is overwritten with the
+    result like the reference does (lib/bundle_entropy.py:200,228).
+    ``state``: a BundleState of a previous call with the same shape to reuse (no device allocation;
+    the lazy A/b/lam/xs views of that earlier call become invalid).  ``stats=True`` collects the
+    per-iteration statistics (``return_state=True`` -> ``state.stats()``).
+    NVTX ranges ``icnn:h2d``, ``icnn:loop``, ``icnn:d2h`` bracket the phases for nsys / ncu.
     """
     if variant not in VARIANT_DEFAULTS:
         raise ValueError("variant must be one of %s" % sorted(VARIANT_DEFAULTS))
@@ -181,19 +247,37 @@ def solveBatch(fg, initXs, nIter=None, callback=None, solver="pc", *, variant="l
     x0 = initXs
     B, n = x0.shape
     if B == 0 or nIter < 1:
-        return (_to_numpy(x0), [[] for _ in range(B)], [[] for _ in range(B)], [None] * B,
-                [[] for _ in range(B)], [nIter] * B)
+        out = (_to_numpy(x0), [[] for _ in range(B)], [[] for _ in range(B)], [None] * B,
+               [[] for _ in range(B)], [nIter] * B)
+        if return_state:   # an empty shard of a sharded batch still gets a (zero-row) state
+            KS0 = max((nIter if variant == "rl" else min(max(nIter, 1), n)) + 1, 2)
+            return out + (_EmptyState(n, KS0, dev),)
+        return out
     # slot capacity: active rows <= min(nIter, n) for the rank-tested copies, + 1 free slot
     KS = (nIter if variant == "rl" else min(nIter, n)) + 1
     KS = max(KS, 2)
+    if KS > 64:
+        # the per-sample k x k algebra lives in one warp's registers / shared memory (include/icnn_b200.h)
+        raise ValueError("solveBatch: min(nIter, n_y) + 1 = %d bundle slots requested, the device solver "
+                         "holds at most 64 (nIter <= 63); the reference has no cap (lib/bundle_entropy.py:192)"
+                         % KS)
     cfg = _make_cfg(variant, solver, nIter, line_search, rank_tol, max_inner, n, KS)
+    f64_cb = False
     with torch.cuda.device(dev):
-        st = BundleState(B, n, KS, dev, keep_xs=keep_xs, nIter=nIter)
-        if isinstance(x0, torch.Tensor):
-            st.y.copy_(x0.to(device=dev, dtype=torch.float64))
+        need = (B, n, KS, dev, keep_xs, nIter, stats, False)
+        if state is not None and state.compatible(*need):
+            st = state
+            st.reset_views()
         else:
-            st.y.copy_(torch.from_numpy(np.ascontiguousarray(x0, dtype=np.float64)), non_blocking=False)
+            st = BundleState(B, n, KS, dev, keep_xs=keep_xs, nIter=nIter, stats=stats)
+        with _nvtx("icnn:h2d"):
+            if isinstance(x0, torch.Tensor):
+                st.y.copy_(x0.to(device=dev, dtype=torch.float64, non_blocking=True))
+            else:
+                st.y.copy_(torch.from_numpy(np.ascontiguousarray(x0, dtype=np.float64)), non_blocking=False)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        loop_rng = _nvtx("icnn:loop")
+        loop_rng.__enter__()
         if fused and callback is None:
             if fg.B != B or fg.net.n != n:
                 raise ValueError("fg is bound to a [%d, %d] problem, initXs is %s" % (fg.B, fg.net.n, (B, n)))
@@ -217,23 +301,41 @@ def solveBatch(fg, initXs, nIter=None, callback=None, solver="pc", *, variant="l
                 else:
                     xi = st.y.cpu().numpy()
                     fi, gi = fg(xi)
-                    if t == 0 and rank_tol is None and variant != "rl" and _dtype_of(gi) == np.float32:
-                        # np.linalg.matrix_rank scales its tolerance with the dtype of the rows: a
-                        # float32 fg (the reference's TF fetch) stops samples at max(k, n) * eps32
-                        cfg.rank_tol = float(max(KS, n) * np.finfo(np.float32).eps)
+                    if t == 0:
+                        f64_cb = (_dtype_of(gi) == np.float64 or _dtype_of(fi) == np.float64)
+                        if f64_cb and st.f64 is None:
+                            # a float64 fg: keep f in float64 for the cut offsets h = f - g.y, like the
+                            # reference (lib/bundle_entropy.py:205-207); the rows themselves are stored
+                            # in float32 (documented deviation)
+                            st.f64 = torch.empty(B, dtype=torch.float64, device=dev)
+                            st.c.f64 = st.f64.data_ptr()
+                        if rank_tol is None and variant != "rl":
+                            # np.linalg.matrix_rank scales its tolerance with the dtype of the rows.  The
+                            # rows are STORED in float32 whatever fg returns, so the tolerance follows the
+                            # storage precision: max(k, n) * eps32 (a float32 fg -- the reference's TF
+                            # fetch -- gets exactly the reference's tolerance; for a float64 fg, rows that
+                            # are dependent in float64 stay detectable after rounding)
+                            cfg.rank_tol = float(max(KS, n) * np.finfo(np.float32).eps)
                     if callback is not None:
                         if variant == "rl":
                             callback(t, _to_numpy(fi))
                         else:
                             callback(t, _to_numpy(fi), xi)
-                    fd = torch.as_tensor(fi, device=dev).to(torch.float32).contiguous().reshape(B)
-                    gd = torch.as_tensor(gi, device=dev).to(torch.float32).contiguous().reshape(B, n)
-                    _capi.check(_capi.lib.icnn_bundle_put_fg(C.byref(st.c), fd.data_ptr(), gd.data_ptr(), stream))
+                    if f64_cb:
+                        fd = torch.as_tensor(fi, device=dev).to(torch.float64).contiguous().reshape(B)
+                        gd = torch.as_tensor(gi, device=dev).to(torch.float64).contiguous().reshape(B, n)
+                        _capi.check(_capi.lib.icnn_bundle_put_fg_f64(C.byref(st.c), fd.data_ptr(), gd.data_ptr(), stream))
+                    else:
+                        fd = torch.as_tensor(fi, device=dev).to(torch.float32).contiguous().reshape(B)
+                        gd = torch.as_tensor(gi, device=dev).to(torch.float32).contiguous().reshape(B, n)
+                        _capi.check(_capi.lib.icnn_bundle_put_fg(C.byref(st.c), fd.data_ptr(), gd.data_ptr(), stream))
                 _capi.check(_capi.lib.icnn_bundle_step(C.byref(cfg), C.byref(st.c), t, stream))
                 if int(st.nactive[t + 1].item()) == 0:   # lib/bundle_entropy.py:239
                     break
-        x = st.y.cpu().numpy()
-        status = st.status.cpu().numpy()
+        loop_rng.__exit__(None, None, None)
+        with _nvtx("icnn:d2h"):
+            x = st.y_host(out=x0 if isinstance(x0, torch.Tensor) else None)
+            status = st.status.cpu().numpy()
     if np.any(status == _capi.ST_NONFINITE) or np.any(status == _capi.ST_SOLVE_FAIL):
         msg = "solveBatch: %d samples non-finite, %d with a failed inner solve" % (
             int(np.sum(status == _capi.ST_NONFINITE)), int(np.sum(status == _capi.ST_SOLVE_FAIL)))

@@ -1,0 +1,93 @@
+// K2 predictor-corrector path: launch configuration + instantiations (WPS = 1, 2); the larger groups are
+// instantiated in bundle_pc_b.cu / bundle_pc_c.cu so that `make -j` compiles them in parallel.
+#include "bundle_pc_kernel.cuh"
+
+#include <cstdlib>
+
+namespace icnn {
+
+#define ICNN_PC_DECL(W, N) cudaError_t launch_pc_##W##_##N(const PcArgs& a, const PcConfig& c, int B, cudaStream_t st)
+ICNN_PC_DECL(1, 1); ICNN_PC_DECL(1, 2); ICNN_PC_DECL(2, 1); ICNN_PC_DECL(2, 2);
+ICNN_PC_DECL(4, 1); ICNN_PC_DECL(4, 2); ICNN_PC_DECL(8, 1); ICNN_PC_DECL(8, 2);
+ICNN_PC_DECL(16, 1); ICNN_PC_DECL(16, 2); ICNN_PC_DECL(16, 4);
+// n_y % 4 != 0 (rows not 16-byte aligned): scalar row loads, small groups only (bundle_pc_d.cu)
+ICNN_PC_DECL(101, 1); ICNN_PC_DECL(101, 2); ICNN_PC_DECL(102, 1); ICNN_PC_DECL(102, 2);
+
+ICNN_PC_DECL(1, 1) { return launch_pc<1, 1, true>(a, c, B, st); }
+ICNN_PC_DECL(1, 2) { return launch_pc<1, 2, true>(a, c, B, st); }
+ICNN_PC_DECL(2, 1) { return launch_pc<2, 1, true>(a, c, B, st); }
+ICNN_PC_DECL(2, 2) { return launch_pc<2, 2, true>(a, c, B, st); }
+
+static bool pc_fits(const icnn_bundle_bufs* b, int wps, int nch, PcConfig* out) {
+  if (b->n > 128 * wps * nch) return false;
+  PcConfig c;
+  c.wps = wps; c.nch = nch;
+  c.npad = (b->n + 15) & ~15;   // the tensor-core sweep reads whole 16-column groups of the n-vectors
+  c.vec = (b->n & 3) == 0;
+  if (!c.vec && wps > 2) return false;
+  const int gpb = wps >= 8 ? 1 : 8 / wps;
+  c.smem = sizeof(double) * pc_group_doubles(c.npad, b->KS, wps) * gpb;
+  if (c.smem > 227 * 1024) return false;
+  c.minb = (wps == 16) ? 1 : ((c.smem + 1024) * 3 <= 228 * 1024 ? 3 : 2);
+  *out = c;
+  return true;
+}
+
+// Threads per sample by n_y (measured per shape): the thread that owns a column in
+// sweep B keeps v2 in registers, so n <= 128 * WPS * NCH.
+static bool pick_pc(const icnn_bundle_bufs* b, PcConfig* out) {
+  const int n = b->n;
+  if (b->KS > 62) return false;   // k + 2 sweep rows in <= 8 row blocks
+  int wps, nch;
+  if (n <= 128) { wps = 1; nch = 1; }
+  else if (n <= 256) { wps = 1; nch = 2; }
+  else if (n <= 512) { wps = 2; nch = 2; }
+  else if (n <= 1024) { wps = 4; nch = 2; }
+  else if (n <= 2048) { wps = 8; nch = 2; }
+  else if (n <= 4096) { wps = 16; nch = 2; }
+  else { wps = 16; nch = 4; }
+  if (const char* v = getenv("ICNN_PC_WPS")) {
+    const int w = atoi(v);
+    if (w == 1 || w == 2 || w == 4 || w == 8 || w == 16) {
+      wps = w;
+      nch = (n <= 128 * w) ? 1 : (n <= 256 * w ? 2 : 4);
+    }
+  }
+  if (nch == 4 && wps != 16) return false;
+  return pc_fits(b, wps, nch, out);
+}
+
+// returns ICNN_E_UNSUPPORTED when the shape has to take the streaming kernel of bundle_step_kernel.cuh
+int bundle_pc_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int t, cudaStream_t st) {
+  PcConfig c;
+  if (!pick_pc(b, &c)) return ICNN_E_UNSUPPORTED;
+  PcArgs a;
+  a.b = *b; a.c = *cfg; a.t = t; a.npad = c.npad;
+  cudaError_t e;
+  const int key = (c.vec ? 0 : 1000) + c.wps * 10 + c.nch;
+  switch (key) {
+    case 1011: e = launch_pc_101_1(a, c, b->B, st); break;
+    case 1012: e = launch_pc_101_2(a, c, b->B, st); break;
+    case 1021: e = launch_pc_102_1(a, c, b->B, st); break;
+    case 1022: e = launch_pc_102_2(a, c, b->B, st); break;
+    case 11: e = launch_pc_1_1(a, c, b->B, st); break;
+    case 12: e = launch_pc_1_2(a, c, b->B, st); break;
+    case 21: e = launch_pc_2_1(a, c, b->B, st); break;
+    case 22: e = launch_pc_2_2(a, c, b->B, st); break;
+    case 41: e = launch_pc_4_1(a, c, b->B, st); break;
+    case 42: e = launch_pc_4_2(a, c, b->B, st); break;
+    case 81: e = launch_pc_8_1(a, c, b->B, st); break;
+    case 82: e = launch_pc_8_2(a, c, b->B, st); break;
+    case 161: e = launch_pc_16_1(a, c, b->B, st); break;
+    case 162: e = launch_pc_16_2(a, c, b->B, st); break;
+    case 164: e = launch_pc_16_4(a, c, b->B, st); break;
+    default: return ICNN_E_UNSUPPORTED;
+  }
+  if (e != cudaSuccess) {
+    set_error("bundle_pc launch (wps=%d nch=%d smem=%zu): %s", c.wps, c.nch, c.smem, cudaGetErrorString(e));
+    return ICNN_E_CUDA;
+  }
+  return ICNN_OK;
+}
+
+}  // namespace icnn

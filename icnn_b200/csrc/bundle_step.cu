@@ -19,6 +19,7 @@ __global__ void bundle_init_kernel(icnn_bundle_bufs b, int nIterMax, int nIterDe
     if (b.ksum) b.ksum[i] = 0;
   }
   if (i <= nIterMax) b.nactive[i] = (i == 0) ? b.B : 0;
+  if (b.iter_stats && i < (long long)nIterMax * ICNN_NSTAT) b.iter_stats[i] = 0.0;
 }
 
 __global__ void y_round_kernel(const double* y, float* y32, long long N) {
@@ -32,6 +33,14 @@ __global__ void put_fg_kernel(icnn_bundle_bufs b, const float* f, const float* g
   float* dst = b.G + ((size_t)u * b.KS + slot) * b.n;
   for (int e = threadIdx.x; e < b.n; e += blockDim.x) dst[e] = gsrc[(size_t)u * b.n + e];
   if (threadIdx.x == 0) b.f[u] = f[u];
+}
+
+__global__ void put_fg64_kernel(icnn_bundle_bufs b, const double* f, const double* gsrc, double* f64) {
+  const int u = blockIdx.x;
+  const int slot = b.perm[(size_t)u * b.KS + b.count[u]];
+  float* dst = b.G + ((size_t)u * b.KS + slot) * b.n;
+  for (int e = threadIdx.x; e < b.n; e += blockDim.x) dst[e] = (float)gsrc[(size_t)u * b.n + e];
+  if (threadIdx.x == 0) { b.f[u] = (float)f[u]; f64[u] = f[u]; }
 }
 
 // Launch configuration: warps per sample (WPS), cluster size over columns (CS) and whether the
@@ -96,12 +105,23 @@ cudaError_t bundle_step_cluster_launch(const StepArgs& a, const K2Config& c, int
 bool bundle_step_small_ok(const icnn_bundle_bufs* b);
 int bundle_step_small_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int t, cudaStream_t st);
 
+int bundle_pc_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int t, cudaStream_t st);
+
 int bundle_step_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int t, cudaStream_t st) {
   {  // tiny problems: one thread per sample (bundle_step_small.cu); ICNN_K2_SMALL=0 forces the group kernel
     const char* v = getenv("ICNN_K2_SMALL");
     if (!(v && v[0] == '0') && bundle_step_small_ok(b)) return bundle_step_small_launch(cfg, b, t, st);
   }
   if (b->KS > 64) { set_error("bundle_step: KS=%d > 64 unsupported", b->KS); return ICNN_E_UNSUPPORTED; }
+  if (cfg->solver == ICNN_SOLVER_PC) {
+    // predictor-corrector: the two-sweep kernel (bundle_pc_kernel.cuh); ICNN_K2_PC=legacy keeps the
+    // five-sweep kernel below (also the fallback for shapes the two-sweep kernel does not cover)
+    const char* v = getenv("ICNN_K2_PC");
+    if (!(v && v[0] == 'l')) {
+      const int rc = bundle_pc_launch(cfg, b, t, st);
+      if (rc != ICNN_E_UNSUPPORTED) return rc;
+    }
+  }
   K2Config c;
   int rc = pick_k2(b, &c);
   if (rc) return rc;
@@ -140,6 +160,7 @@ extern "C" int icnn_bundle_init(const icnn_bundle_bufs* b, int32_t nIterMax, voi
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long tot = (long long)b->B * b->KS;
   if (tot < nIterMax + 1) tot = nIterMax + 1;
+  if (tot < (long long)nIterMax * ICNN_NSTAT) tot = (long long)nIterMax * ICNN_NSTAT;
   bundle_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(*b, nIterMax, nIterMax);
   const long long N = (long long)b->B * b->n;
   y_round_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(b->y, b->y32, N);
@@ -152,6 +173,16 @@ extern "C" int icnn_bundle_put_fg(const icnn_bundle_bufs* b, const float* f, con
   if (rc) return rc;
   ICNN_REQUIRE(f && g, "null f/g");
   put_fg_kernel<<<b->B, 128, 0, static_cast<cudaStream_t>(stream)>>>(*b, f, g);
+  ICNN_CUDA_CHECK(cudaGetLastError());
+  return ICNN_OK;
+}
+
+extern "C" int icnn_bundle_put_fg_f64(const icnn_bundle_bufs* b, const double* f, const double* g, void* stream) {
+  int rc = check_bufs(b);
+  if (rc) return rc;
+  ICNN_REQUIRE(f && g, "null f/g");
+  ICNN_REQUIRE(b->f64, "icnn_bundle_put_fg_f64 needs bufs.f64");
+  put_fg64_kernel<<<b->B, 128, 0, static_cast<cudaStream_t>(stream)>>>(*b, f, g, const_cast<double*>(b->f64));
   ICNN_CUDA_CHECK(cudaGetLastError());
   return ICNN_OK;
 }

@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(WPS == 16 ? 512 : 256, MINB) bundle_step_kerne
 
   // ---- append: h = f - g.y ; row sum ; unweighted Gram row ; xs copy ; non-finite guard ------
   {
-    double hs = 0.0, rs = 0.0, bad = 0.0;
+    double hs = 0.0, rs = 0.0, bad = 0.0, ent = 0.0;
     double* ysrow = b.ys ? b.ys + ((size_t)u * KS + slot_new) * nglob + c0 : nullptr;
     for (int e = g.tid; e < n; e += T) {
       const double ge = (double)gnew[e];
@@ -581,13 +581,16 @@ __global__ void __launch_bounds__(WPS == 16 ? 512 : 256, MINB) bundle_step_kerne
       rs += ge;
       if (!isfinite(ge)) bad = 1.0;
       if (ysrow) ysrow[e] = ye;
+      if (b.iter_stats) ent += neg_entropy(ye);
     }
+    if (b.iter_stats) ent = g.csum(ent);
     hs = g.csum(hs);
     rs = g.csum(rs);
     bad = g.cmax(bad);
-    const double fu = (double)b.f[u];
+    const double fu = b.f64 ? b.f64[u] : (double)b.f[u];
+    if (g.tid == 0 && lead) { stat_add(b.iter_stats, A.t, 0, 1.0); stat_add(b.iter_stats, A.t, 6, fu + ent); }
     if (bad > 0.0 || !isfinite(fu)) {
-      if (g.tid == 0 && lead) { b.status[u] = ICNN_ST_NONFINITE; b.finished[u] = 1; b.nIters[u] = A.t - 1; }
+      if (g.tid == 0 && lead) { b.status[u] = ICNN_ST_NONFINITE; b.finished[u] = 1; b.nIters[u] = A.t - 1; stat_add(b.iter_stats, A.t, 5, 1.0); }
       return;
     }
     // Gram row of the new row against all active rows (row pass), plus exact-duplicate detection
@@ -677,7 +680,7 @@ __global__ void __launch_bounds__(WPS == 16 ? 512 : 256, MINB) bundle_step_kerne
     }
     if (dependent) {
       // pop the row, mark finished, nIters = t-1 (lib/bundle_entropy.py:220-225); y unchanged
-      if (g.tid == 0 && lead) { b.status[u] = ICNN_ST_RANK_STOP; b.finished[u] = 1; b.nIters[u] = A.t - 1; }
+      if (g.tid == 0 && lead) { b.status[u] = ICNN_ST_RANK_STOP; b.finished[u] = 1; b.nIters[u] = A.t - 1; stat_add(b.iter_stats, A.t, 5, 1.0); }
       return;
     }
   }
@@ -1068,7 +1071,7 @@ __global__ void __launch_bounds__(WPS == 16 ? 512 : 256, MINB) bundle_step_kerne
     b.count[u] = nk;
     int fin = 0;
     int stt = ICNN_ST_RUNNING;
-    if (fail) stt = ICNN_ST_SOLVE_FAIL;
+    if (fail || b.status[u] == ICNN_ST_SOLVE_FAIL) stt = ICNN_ST_SOLVE_FAIL;   // sticky: an earlier failed inner solve stays visible
     if (bad > 0.0) { stt = ICNN_ST_NONFINITE; fin = 1; }
     if (rl && maxdiff < 1e-6) { fin = 1; if (stt == ICNN_ST_RUNNING) stt = ICNN_ST_CONVERGED; }
     b.status[u] = stt;
@@ -1076,6 +1079,13 @@ __global__ void __launch_bounds__(WPS == 16 ? 512 : 256, MINB) bundle_step_kerne
     else atomicAdd(&b.nactive[A.t + 1], 1);
     if (b.newton_its) b.newton_its[u] += inner_its;
     if (b.ksum) b.ksum[u] += k;
+    if (b.iter_stats) {
+      stat_add(b.iter_stats, A.t, 1, (double)k);
+      stat_add(b.iter_stats, A.t, 2, (double)inner_its);
+      stat_add(b.iter_stats, A.t, 3, (double)inner_its * k * k);
+      stat_add(b.iter_stats, A.t, 4, (double)inner_its * k);
+      if (fin) stat_add(b.iter_stats, A.t, 5, 1.0);
+    }
   }
 }
 

@@ -82,9 +82,15 @@ __global__ void __launch_bounds__(128) bundle_step_small_kernel(SmallArgs A) {
   double hs = 0.0, rs = 0.0;
   bool bad = false;
   for (int e = 0; e < n; ++e) { hs = fma(G[k0][e], y[e], hs); rs += G[k0][e]; bad |= !isfinite(G[k0][e]); }
-  const double fu = (double)b.f[u];
+  const double fu = b.f64 ? b.f64[u] : (double)b.f[u];
+  if (b.iter_stats) {
+    double ent = 0.0;
+    for (int e = 0; e < n; ++e) ent += neg_entropy(y[e]);
+    stat_add(b.iter_stats, A.t, 0, 1.0);
+    stat_add(b.iter_stats, A.t, 6, fu + ent);
+  }
   if (b.ys) { double* ysrow = b.ys + ((size_t)u * KS + slot_new) * n; for (int e = 0; e < n; ++e) ysrow[e] = y[e]; }
-  if (bad || !isfinite(fu)) { b.status[u] = ICNN_ST_NONFINITE; b.finished[u] = 1; b.nIters[u] = A.t - 1; return; }
+  if (bad || !isfinite(fu)) { b.status[u] = ICNN_ST_NONFINITE; b.finished[u] = 1; b.nIters[u] = A.t - 1; stat_add(b.iter_stats, A.t, 5, 1.0); return; }
   double tk[KM];
   bool dup = false;
   for (int j = 0; j < k; ++j) {
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(128) bundle_step_small_kernel(SmallArgs A) {
         }
       }
     } else dependent = !(tk[0] > 0.0);
-    if (dependent) { b.status[u] = ICNN_ST_RANK_STOP; b.finished[u] = 1; b.nIters[u] = A.t - 1; return; }
+    if (dependent) { b.status[u] = ICNN_ST_RANK_STOP; b.finished[u] = 1; b.nIters[u] = A.t - 1; stat_add(b.iter_stats, A.t, 5, 1.0); return; }
   }
   for (int j = 0; j < k; ++j) { gramu[(size_t)slot_new * KS + sl[j]] = tk[j]; gramu[(size_t)sl[j] * KS + slot_new] = tk[j]; }
 
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(128) bundle_step_small_kernel(SmallArgs A) {
   for (int j = 0; j < nd; ++j) permu[nk + j] = dropped[j];
   b.count[u] = nk;
   int fin = 0, stt = ICNN_ST_RUNNING;
-  if (fail) stt = ICNN_ST_SOLVE_FAIL;
+  if (fail || b.status[u] == ICNN_ST_SOLVE_FAIL) stt = ICNN_ST_SOLVE_FAIL;   // sticky: an earlier failed inner solve stays visible
   if (nf_bad) { stt = ICNN_ST_NONFINITE; fin = 1; }
   if (rl && maxdiff < 1e-6) { fin = 1; if (stt == ICNN_ST_RUNNING) stt = ICNN_ST_CONVERGED; }
   b.status[u] = stt;
@@ -344,6 +350,13 @@ __global__ void __launch_bounds__(128) bundle_step_small_kernel(SmallArgs A) {
   else atomicAdd(&b.nactive[A.t + 1], 1);
   if (b.newton_its) b.newton_its[u] += inner_its;
   if (b.ksum) b.ksum[u] += k;
+  if (b.iter_stats) {
+    stat_add(b.iter_stats, A.t, 1, (double)k);
+    stat_add(b.iter_stats, A.t, 2, (double)inner_its);
+    stat_add(b.iter_stats, A.t, 3, (double)inner_its * k * k);
+    stat_add(b.iter_stats, A.t, 4, (double)inner_its * k);
+    if (fin) stat_add(b.iter_stats, A.t, 5, 1.0);
+  }
 }
 
 bool bundle_step_small_ok(const icnn_bundle_bufs* b) { return b->n <= NM && b->KS <= KM; }

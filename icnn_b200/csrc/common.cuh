@@ -32,6 +32,19 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+#ifdef __CUDACC__
+// optional per-outer-iteration statistics (icnn_bundle_bufs::iter_stats), totals over samples
+__device__ __forceinline__ void stat_add(double* st, int t, int idx, double v) {
+  if (st) atomicAdd(st + (size_t)t * ICNN_NSTAT + idx, v);
+}
+// y log y + (1 - y) log(1 - y) with 0 log 0 = 0  (negative entropy of one coordinate, ebundle-vs-gd.py:38-41)
+__device__ __forceinline__ double neg_entropy(double y) {
+  double a = 0.0;
+  if (y > 0.0) a += y * log(y);
+  if (y < 1.0) a += (1.0 - y) * log(1.0 - y);
+  return a;
+}
+#endif
 // leading dimension padded to 4 floats: 16-byte row pitch for TMA; the pad columns lie outside the
 // tensor map's extent (TMA zero-fills them), so they are never read and need no initialisation
 static inline int ld4(int k) { return (k + 3) & ~3; }

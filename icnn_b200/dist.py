@@ -10,6 +10,7 @@ GPUs, gloo in the CPU tests) is the plumbing.
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -53,9 +54,15 @@ def solve_batch_sharded(net, x, y0, nIter=None, solver="pc", variant="lib", affi
     rank, ws = dist.get_rank(group), dist.get_world_size(group)
     B = x.shape[0]
     lo, hi = shard_rows(B, rank, ws)
-    fg = net.bind(x[lo:hi], affine=affine)
-    out = bundle_entropy.solveBatch(fg, y0[lo:hi].copy(), nIter=nIter, solver=solver, variant=variant,
-                                    return_state=True, **kw)
+    y0b = y0[lo:hi]
+    y0b = y0b.clone() if isinstance(y0b, torch.Tensor) else np.array(y0b, dtype=np.float64)
+    if hi > lo:
+        fg = net.bind(x[lo:hi], affine=affine)
+        out = bundle_entropy.solveBatch(fg, y0b, nIter=nIter, solver=solver, variant=variant,
+                                        return_state=True, **kw)
+    else:   # B < world_size: this rank owns no rows but still takes part in the gather below
+        out = bundle_entropy.solveBatch(None, y0b, nIter=nIter, solver=solver, variant=variant,
+                                        return_state=True, device=net.device, **kw)
     st = out[-1]
     y_all = allgather_rows(st.y, B, group=group)
     return y_all, out[:-1]

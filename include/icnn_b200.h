@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ICNN_ABI_VERSION 1
+#define ICNN_ABI_VERSION 2
 
 #define ICNN_OK 0
 #define ICNN_E_INVALID (-1)  /* bad argument */
@@ -98,7 +98,19 @@ typedef struct {
   int32_t* newton_its; /* [B] accumulated inner (IPM / Newton) iterations, diagnostics */
   int32_t* ksum;     /* [B] sum over executed iterations of the active row count k_t
                         (algorithmic-bytes accounting for the roofline) */
+  const double* f64; /* [B] optional (may be NULL): f(y) in float64.  When set, h = f - g.y is formed from
+                        it instead of the float32 f -- callback mode with a float64 fg, whose f the
+                        reference keeps in float64 (lib/bundle_entropy.py:205-207)                      */
+  double* iter_stats; /* [nIterMax, ICNN_NSTAT] optional (may be NULL): per-outer-iteration totals over the
+                        samples solved in that iteration, accumulated with atomics (SURVEY.md section 5:
+                        what the reference prints / plots per iteration, ebundle-vs-gd.py:94-99):
+                        [0] samples entering the solve   [1] sum of active rows k      [2] sum of inner
+                        (IPM / Newton) iterations        [3] sum of inner_its * k^2    [4] sum of inner_its * k
+                        [5] samples stopped in this iteration (rank / convergence / non-finite)
+                        [6] sum of f(y_t) - H(y_t) over the samples entering the iteration (0 log 0 = 0)
+                        [7] reserved                                                                  */
 } icnn_bundle_bufs;
+#define ICNN_NSTAT 8
 
 typedef struct {
   int32_t variant;     /* ICNN_VARIANT_*                                               */
@@ -152,6 +164,10 @@ int icnn_picnn_gates(const icnn_picnn_t* h, const float* x, int32_t B, float* co
 int icnn_bundle_init(const icnn_bundle_bufs* b, int32_t nIterMax, void* stream);
 /* callback mode: scatter a dense g [B, n] (device, float32) into the free slots and f [B] */
 int icnn_bundle_put_fg(const icnn_bundle_bufs* b, const float* f, const float* g, void* stream);
+/* same for a float64 fg (the reference keeps whatever dtype fg returns and forms b = f - sum(g x) in
+ * float64, lib/bundle_entropy.py:205-207): rows are rounded to the float32 row storage, f is kept in
+ * float64 in b->f64 (which must be set) so that the cut offset h = f - g.y is formed from the float64 f. */
+int icnn_bundle_put_fg_f64(const icnn_bundle_bufs* b, const double* f, const double* g, void* stream);
 /* one outer iteration t for every unfinished sample: append row, dependency test, solve,
  * y update, prune.  f and the new row must already be in place. */
 int icnn_bundle_step(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int32_t t, void* stream);

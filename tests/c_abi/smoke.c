@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "icnn_b200.h"
 
@@ -58,7 +59,8 @@ int main(void) {
   if (!(maxerr < 1e-4)) return 4;
 
   /* one bundle step through the ABI */
-  icnn_bundle_bufs bb; bb.B = B; bb.n = N; bb.KS = KS;
+  icnn_bundle_bufs bb; memset(&bb, 0, sizeof bb);   /* optional members (f64, iter_stats) = NULL */
+  bb.B = B; bb.n = N; bb.KS = KS;
   double yh[B * N]; for (int i = 0; i < B * N; ++i) yh[i] = y[i];
   CK(cudaMalloc((void**)&bb.y, B * N * 8)); CK(cudaMemcpy(bb.y, yh, sizeof yh, cudaMemcpyHostToDevice));
   CK(cudaMalloc((void**)&bb.y32, B * N * 4)); CK(cudaMalloc((void**)&bb.f, B * 4)); CK(cudaMalloc((void**)&bb.G, B * KS * N * 4));
