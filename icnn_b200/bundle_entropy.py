@@ -263,6 +263,7 @@ def solveBatch(fg, initXs, nIter=None, callback=None, solver="pc", *, variant="l
                          % KS)
     cfg = _make_cfg(variant, solver, nIter, line_search, rank_tol, max_inner, n, KS)
     f64_cb = False
+    rows_inexact = False
     with torch.cuda.device(dev):
         need = (B, n, KS, dev, keep_xs, nIter, stats, False)
         if state is not None and state.compatible(*need):
@@ -309,12 +310,9 @@ def solveBatch(fg, initXs, nIter=None, callback=None, solver="pc", *, variant="l
                             # in float32 (documented deviation)
                             st.f64 = torch.empty(B, dtype=torch.float64, device=dev)
                             st.c.f64 = st.f64.data_ptr()
-                        if rank_tol is None and variant != "rl":
-                            # np.linalg.matrix_rank scales its tolerance with the dtype of the rows.  The
-                            # rows are STORED in float32 whatever fg returns, so the tolerance follows the
-                            # storage precision: max(k, n) * eps32 (a float32 fg -- the reference's TF
-                            # fetch -- gets exactly the reference's tolerance; for a float64 fg, rows that
-                            # are dependent in float64 stay detectable after rounding)
+                        if rank_tol is None and variant != "rl" and _dtype_of(gi) == np.float32:
+                            # np.linalg.matrix_rank scales its tolerance with the dtype of the rows: a
+                            # float32 fg (the reference's TF fetch) stops samples at max(k, n) * eps32
                             cfg.rank_tol = float(max(KS, n) * np.finfo(np.float32).eps)
                     if callback is not None:
                         if variant == "rl":
@@ -324,6 +322,14 @@ def solveBatch(fg, initXs, nIter=None, callback=None, solver="pc", *, variant="l
                     if f64_cb:
                         fd = torch.as_tensor(fi, device=dev).to(torch.float64).contiguous().reshape(B)
                         gd = torch.as_tensor(gi, device=dev).to(torch.float64).contiguous().reshape(B, n)
+                        if rank_tol is None and variant != "rl" and not rows_inexact \
+                                and bool((gd.to(torch.float32).to(torch.float64) != gd).any()):
+                            # genuinely float64 rows do not survive the float32 row storage exactly: from here
+                            # on the dependency test works at the storage precision, max(k, n) * eps32, so
+                            # that rows dependent in float64 are still detected after rounding (rows that are
+                            # float32-representable keep the reference's float64 tolerance)
+                            rows_inexact = True
+                            cfg.rank_tol = float(max(KS, n) * np.finfo(np.float32).eps)
                         _capi.check(_capi.lib.icnn_bundle_put_fg_f64(C.byref(st.c), fd.data_ptr(), gd.data_ptr(), stream))
                     else:
                         fd = torch.as_tensor(fi, device=dev).to(torch.float32).contiguous().reshape(B)

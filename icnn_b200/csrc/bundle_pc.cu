@@ -7,7 +7,7 @@
 namespace icnn {
 
 #define ICNN_PC_DECL(W, N) cudaError_t launch_pc_##W##_##N(const PcArgs& a, const PcConfig& c, int B, cudaStream_t st)
-ICNN_PC_DECL(1, 1); ICNN_PC_DECL(1, 2); ICNN_PC_DECL(2, 1); ICNN_PC_DECL(2, 2);
+ICNN_PC_DECL(1, 1); ICNN_PC_DECL(1, 2); ICNN_PC_DECL(1, 4); ICNN_PC_DECL(2, 1); ICNN_PC_DECL(2, 2);
 ICNN_PC_DECL(4, 1); ICNN_PC_DECL(4, 2); ICNN_PC_DECL(8, 1); ICNN_PC_DECL(8, 2);
 ICNN_PC_DECL(16, 1); ICNN_PC_DECL(16, 2); ICNN_PC_DECL(16, 4);
 // n_y % 4 != 0 (rows not 16-byte aligned): scalar row loads, small groups only (bundle_pc_d.cu)
@@ -15,6 +15,7 @@ ICNN_PC_DECL(101, 1); ICNN_PC_DECL(101, 2); ICNN_PC_DECL(102, 1); ICNN_PC_DECL(1
 
 ICNN_PC_DECL(1, 1) { return launch_pc<1, 1, true>(a, c, B, st); }
 ICNN_PC_DECL(1, 2) { return launch_pc<1, 2, true>(a, c, B, st); }
+ICNN_PC_DECL(1, 4) { return launch_pc<1, 4, true>(a, c, B, st); }
 ICNN_PC_DECL(2, 1) { return launch_pc<2, 1, true>(a, c, B, st); }
 ICNN_PC_DECL(2, 2) { return launch_pc<2, 2, true>(a, c, B, st); }
 
@@ -25,10 +26,12 @@ static bool pc_fits(const icnn_bundle_bufs* b, int wps, int nch, PcConfig* out) 
   c.npad = (b->n + 15) & ~15;   // the tensor-core sweep reads whole 16-column groups of the n-vectors
   c.vec = (b->n & 3) == 0;
   if (!c.vec && wps > 2) return false;
-  const int gpb = wps >= 8 ? 1 : 8 / wps;
-  c.smem = sizeof(double) * pc_group_doubles(c.npad, b->KS, wps) * gpb;
+  c.smem = sizeof(double) * pc_group_doubles(c.npad, b->KS, wps);
   if (c.smem > 227 * 1024) return false;
-  c.minb = (wps == 16) ? 1 : ((c.smem + 1024) * 3 <= 228 * 1024 ? 3 : 2);
+  // 80-register build (768 threads / SM) when shared memory lets that many samples be resident, else 128 registers
+  c.minb = (wps == 16) ? 1 : ((c.smem + 1024) * (24 / wps) <= 228 * 1024 ? 3 : 2);
+  if (wps == 1) c.minb = 2;   // one warp per sample: the 128-register build (no spills) wins (C3 4.5 vs 5.2 ms)
+  if (const char* v = getenv("ICNN_PC_MINB")) { if (v[0] == '2') c.minb = 2; }   // tuning knob: 128-register build
   *out = c;
   return true;
 }
@@ -38,6 +41,12 @@ static bool pc_fits(const icnn_bundle_bufs* b, int wps, int nch, PcConfig* out) 
 static bool pick_pc(const icnn_bundle_bufs* b, PcConfig* out) {
   const int n = b->n;
   if (b->KS > 62) return false;   // k + 2 sweep rows in <= 8 row blocks
+  // measured on B200, K2 ms per solveBatch (profiles/r02_k2_sweep.md):
+  //   n = 159  (C3)            two-sweep WPS 1: 4.5 (128-register build; 5.2 at 80 registers), WPS 2: 6.4; five-sweep 6.9
+  //   n = 512  (T)             two-sweep WPS 1: 10.6, 2: 9.9, 4: 11.0;                                   five-sweep 9.4
+  //   n = 2048 (C2)            two-sweep WPS 8: 20.3, 16: 27.7;                                          five-sweep 19.4
+  //   n = 4096 (C5, 1024 rows) two-sweep WPS 16: 203;                                                    five-sweep 224
+  // -> the two-sweep kernel where it wins (small and very large n_y), the five-sweep kernel in between.
   int wps, nch;
   if (n <= 128) { wps = 1; nch = 1; }
   else if (n <= 256) { wps = 1; nch = 2; }
@@ -46,6 +55,7 @@ static bool pick_pc(const icnn_bundle_bufs* b, PcConfig* out) {
   else if (n <= 2048) { wps = 8; nch = 2; }
   else if (n <= 4096) { wps = 16; nch = 2; }
   else { wps = 16; nch = 4; }
+  if (n > 256 && n <= 2048 && !getenv("ICNN_PC_WPS")) return false;
   if (const char* v = getenv("ICNN_PC_WPS")) {
     const int w = atoi(v);
     if (w == 1 || w == 2 || w == 4 || w == 8 || w == 16) {
@@ -53,7 +63,7 @@ static bool pick_pc(const icnn_bundle_bufs* b, PcConfig* out) {
       nch = (n <= 128 * w) ? 1 : (n <= 256 * w ? 2 : 4);
     }
   }
-  if (nch == 4 && wps != 16) return false;
+  if (nch == 4 && wps != 16 && wps != 1) return false;
   return pc_fits(b, wps, nch, out);
 }
 
@@ -72,6 +82,7 @@ int bundle_pc_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int 
     case 1022: e = launch_pc_102_2(a, c, b->B, st); break;
     case 11: e = launch_pc_1_1(a, c, b->B, st); break;
     case 12: e = launch_pc_1_2(a, c, b->B, st); break;
+    case 14: e = launch_pc_1_4(a, c, b->B, st); break;
     case 21: e = launch_pc_2_1(a, c, b->B, st); break;
     case 22: e = launch_pc_2_2(a, c, b->B, st); break;
     case 41: e = launch_pc_4_1(a, c, b->B, st); break;

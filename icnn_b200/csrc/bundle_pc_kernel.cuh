@@ -190,48 +190,63 @@ __device__ __forceinline__ void gram_sweep_pc(const G& g, const float* const* ro
   const double* yq = yv + 4 * q;
   const double* rq = rv + 4 * q;
   const int ngrp = (n + 15) >> 4;
+  // Two 16-column groups per loop trip when the tile set is small: both groups' row loads are issued before
+  // the tensor-core work (one sample's sweep is otherwise a chain of L2 round trips); with 8+ tiles of
+  // accumulators the second set of row registers would spill.
+  constexpr int NG = (NT <= 6) ? 2 : 1;
 #pragma unroll 1
-  for (int gi = g.warp; gi < ngrp; gi += WPS) {
-    const int off = gi * 16;
-    const int col = off + 4 * q;
-    float4 v[NL];
+  for (int gi = g.warp; gi < ngrp; gi += NG * WPS) {
+    float4 v[NG][NL];
 #pragma unroll
-    for (int b = 0; b < NL; ++b) {
-      v[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (VEC) {
-        if (rok[b] && col < n) v[b] = *reinterpret_cast<const float4*>(rp[b] + off);
-      } else if (rok[b]) {
-        const float* p = rp[b] + off;
-        if (col < n) v[b].x = p[0];
-        if (col + 1 < n) v[b].y = p[1];
-        if (col + 2 < n) v[b].z = p[2];
-        if (col + 3 < n) v[b].w = p[3];
-      }
-    }
-    const double2 ya = *reinterpret_cast<const double2*>(yq + off), yb = *reinterpret_cast<const double2*>(yq + off + 2);
-    double dd[4] = {dweight(ya.x), dweight(ya.y), dweight(yb.x), dweight(yb.y)};
-    double pa[4] = {0.0, 0.0, 0.0, 0.0};
-    if (PSEUDO && ps) {
-      if (r == 0) {
-        const double2 ra = *reinterpret_cast<const double2*>(rq + off), rb = *reinterpret_cast<const double2*>(rq + off + 2);
-        pa[0] = dd[0] * ra.x; pa[1] = dd[1] * ra.y; pa[2] = dd[2] * rb.x; pa[3] = dd[3] * rb.y;
-      } else {
-        pa[0] = ya.x; pa[1] = ya.y; pa[2] = yb.x; pa[3] = yb.y;
+    for (int u = 0; u < NG; ++u) {
+      const int gu = gi + u * WPS;
+      const int off = gu * 16;
+      const int col = off + 4 * q;
+      const bool gv = (u == 0) || gu < ngrp;
+#pragma unroll
+      for (int b = 0; b < NL; ++b) {
+        v[u][b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (VEC) {
+          if (gv && rok[b] && col < n) v[u][b] = *reinterpret_cast<const float4*>(rp[b] + off);
+        } else if (gv && rok[b]) {
+          const float* p = rp[b] + off;
+          if (col < n) v[u][b].x = p[0];
+          if (col + 1 < n) v[u][b].y = p[1];
+          if (col + 2 < n) v[u][b].z = p[2];
+          if (col + 3 < n) v[u][b].w = p[3];
+        }
       }
     }
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      double f[NL];
+    for (int u = 0; u < NG; ++u) {
+      const int gu = gi + u * WPS;
+      if (u > 0 && gu >= ngrp) break;
+      const int off = gu * 16;
+      const double2 ya = *reinterpret_cast<const double2*>(yq + off), yb = *reinterpret_cast<const double2*>(yq + off + 2);
+      double dd[4] = {dweight(ya.x), dweight(ya.y), dweight(yb.x), dweight(yb.y)};
+      double pa[4] = {0.0, 0.0, 0.0, 0.0};
+      if (PSEUDO && ps) {
+        if (r == 0) {
+          const double2 ra = *reinterpret_cast<const double2*>(rq + off), rb = *reinterpret_cast<const double2*>(rq + off + 2);
+          pa[0] = dd[0] * ra.x; pa[1] = dd[1] * ra.y; pa[2] = dd[2] * rb.x; pa[3] = dd[3] * rb.y;
+        } else {
+          pa[0] = ya.x; pa[1] = ya.y; pa[2] = yb.x; pa[3] = yb.y;
+        }
+      }
 #pragma unroll
-      for (int b = 0; b < NL; ++b)
-        f[b] = (double)((s == 0) ? v[b].x : (s == 1) ? v[b].y : (s == 2) ? v[b].z : v[b].w);
-      int t = 0;
+      for (int s = 0; s < 4; ++s) {
+        double f[NL];
 #pragma unroll
-      for (int i = 0; i < NA; ++i) {
-        // pseudo lanes have f[0] = 0 (no bundle row), the others pa = 0: one FMA selects the A value
-        const double af = (PSEUDO && i == 0) ? fma(f[0], dd[s], pa[s]) : f[i] * dd[s];
+        for (int b = 0; b < NL; ++b)
+          f[b] = (double)((s == 0) ? v[u][b].x : (s == 1) ? v[u][b].y : (s == 2) ? v[u][b].z : v[u][b].w);
+        int t = 0;
 #pragma unroll
-        for (int j = TRI ? i : 0; j < NB; ++j) { dmma884(acc[t][0], acc[t][1], af, f[TRI ? j : NA + j]); ++t; }
+        for (int i = 0; i < NA; ++i) {
+          // pseudo lanes have f[0] = 0 (no bundle row), the others pa = 0: one FMA selects the A value
+          const double af = (PSEUDO && i == 0) ? fma(f[0], dd[s], pa[s]) : f[i] * dd[s];
+#pragma unroll
+          for (int j = TRI ? i : 0; j < NB; ++j) { dmma884(acc[t][0], acc[t][1], af, f[TRI ? j : NA + j]); ++t; }
+        }
       }
     }
   }
@@ -374,15 +389,16 @@ __device__ __forceinline__ void ratio_min(double& nm, double& dn, double a, doub
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------
-// WPS warps own one sample (8 / WPS samples per 256-thread CTA for WPS < 8; one CTA per sample for
-// WPS = 8, 16); NCH = chunks of 4 T columns per thread (n <= 4 T NCH).
-template <int WPS, int NCH, int MINB, bool VEC>
-__global__ void __launch_bounds__(WPS == 16 ? 512 : 256, MINB) bundle_pc_kernel(PcArgs A) {
+// One CTA of WPS warps per sample (the block scheduler balances the SMs at sample granularity: with several
+// samples per CTA the last, partly filled wave costs a whole extra round);  NCH = chunks of 4 T columns per
+// thread (n <= 4 T NCH);  R80: 80-register build (768 threads / SM) instead of 128 registers (512 / SM).
+template <int WPS, int NCH, bool R80, bool VEC>
+__global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WPS) bundle_pc_kernel(PcArgs A) {
   const icnn_bundle_bufs& b = A.b;
   const icnn_bundle_cfg& cf = A.c;
   if (b.nactive[A.t] == 0) return;
   extern __shared__ __align__(16) double smem_d[];
-  constexpr int GPB = (WPS >= 8) ? 1 : 8 / WPS;
+  constexpr int GPB = 1;
   constexpr int T = WPS * 32;
   static_assert(NCH == 1 || NCH == 2 || NCH == 4, "NCH");
   Grp<WPS, 1> g;
@@ -791,12 +807,11 @@ struct PcConfig { int wps, nch, npad, minb; bool vec; size_t smem; };
 template <int WPS, int NCH, bool VEC>
 static cudaError_t launch_pc(const PcArgs& a, const PcConfig& c, int B, cudaStream_t st) {
   void (*kern)(PcArgs);
-  if constexpr (WPS == 16) kern = bundle_pc_kernel<16, NCH, 1, VEC>;
-  else kern = (c.minb >= 3) ? bundle_pc_kernel<WPS, NCH, 3, VEC> : bundle_pc_kernel<WPS, NCH, 2, VEC>;
+  if constexpr (WPS == 16) kern = bundle_pc_kernel<16, NCH, false, VEC>;
+  else kern = (c.minb >= 3) ? bundle_pc_kernel<WPS, NCH, true, VEC> : bundle_pc_kernel<WPS, NCH, false, VEC>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
   if (e != cudaSuccess) return e;
-  const int gpb = WPS >= 8 ? 1 : 8 / WPS;
-  kern<<<(unsigned)cdiv(B, gpb), WPS == 16 ? 512 : 256, c.smem, st>>>(a);
+  kern<<<(unsigned)B, WPS * 32, c.smem, st>>>(a);
   return cudaGetLastError();
 }
 
