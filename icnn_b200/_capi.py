@@ -29,7 +29,7 @@ SYMBOLS = [
     "icnn_solve_batch_fused", "icnn_gd_solve", "icnn_tc_gemm_selftest", "icnn_argmin_grad",
     "icnn_picnn_set_xpath", "icnn_picnn_gates_workspace_bytes", "icnn_picnn_gates",
     "icnn_adam_workspace_bytes", "icnn_adam_solve",
-    "icnn_gd_backward_workspace_bytes", "icnn_gd_backward",
+    "icnn_gd_backward_workspace_bytes", "icnn_gd_backward", "icnn_fp64_mma_probe",
 ]
 
 _fpp = C.POINTER(C.c_void_p)
@@ -109,6 +109,7 @@ def _load():
     lib.icnn_gd_backward_workspace_bytes.restype = C.c_size_t
     lib.icnn_gd_backward.argtypes = [C.c_void_p, C.POINTER(Gates), C.c_void_p, C.c_void_p, C.c_float, C.c_int32,
                                      C.c_float, C.c_float, C.c_void_p, C.POINTER(GdGrads), C.c_void_p, C.c_void_p]
+    lib.icnn_fp64_mma_probe.argtypes = [C.c_int32, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
     for name in SYMBOLS:
         getattr(lib, name)  # AttributeError if the .so does not export it
     if lib.icnn_abi_version() != ABI_VERSION:

@@ -32,6 +32,37 @@ extern "C" int icnn_device_count(void) {
   return n;
 }
 
+namespace icnn {
+__global__ void __launch_bounds__(256) fp64_mma_probe_kernel(int iters, double* sink) {
+  double acc[8][2];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t][0] = acc[t][1] = 0.0;
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) s += acc[t][0] + acc[t][1];
+  if (s == 123.456) *sink = s;   // never true: keeps the loop alive
+}
+}  // namespace icnn
+
+extern "C" int icnn_fp64_mma_probe(int32_t iters, double* sink, double* flops_out, void* stream) {
+  ICNN_REQUIRE(iters > 0 && sink && flops_out, "bad arguments");
+  int dev = 0, sms = 0;
+  ICNN_CUDA_CHECK(cudaGetDevice(&dev));
+  ICNN_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8;
+  fp64_mma_probe_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(iters, sink);
+  ICNN_CUDA_CHECK(cudaGetLastError());
+  *flops_out = (double)blocks * 8.0 /* warps */ * (double)iters * 8.0 /* mma */ * 2.0 * 8 * 8 * 4;
+  return ICNN_OK;
+}
+
 extern "C" int icnn_solve_batch_fused(const icnn_picnn_t* h, const icnn_gates* gates, const icnn_bundle_cfg* cfg,
                                       const icnn_bundle_bufs* b, void* workspace, void* stream) {
   ICNN_REQUIRE(h && gates && cfg && b && workspace, "null pointer");

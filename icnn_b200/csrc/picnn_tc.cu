@@ -574,12 +574,12 @@ static int make_tmap(CUtensorMap* tm, const float* base, long long rows, long lo
 template <int BN, int NST_, bool GDB = false>
 static cudaError_t launch_tc_variant(const CUtensorMap& tAh, const CUtensorMap& tAl, const CUtensorMap& tBh,
                                      const CUtensorMap& tBl, const TcArgs& a, int splitk, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  // per device / context attribute: set on every launch (a process-wide "done" flag would leave every device but
+  // the first without it; the call is a host-side table update, ~1 us)
+  {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, NST_, GDB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TcSmem<BN, NST_>::TOTAL);
     if (e != cudaSuccess) return e;
-    attr = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cdiv(a.N, BN), cdiv(a.M, TC_BM), splitk);

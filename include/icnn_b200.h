@@ -233,6 +233,11 @@ int icnn_adam_solve(const icnn_picnn_t* h, const icnn_gates* gates, double* act_
  * scratch holds 2*M*K + 2*N*K floats). */
 int icnn_tc_gemm_selftest(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
                           float* scratch, void* stream);
+/* FP64 tensor-core throughput probe: every warp of a full-chip grid issues `iters` x 8 independent
+ * mma.m8n8k4.f64 (the instruction K2's weighted-Gram sweep is built from); *flops_out (host) = FLOPs the
+ * launch performs, sink (device, 1 double) keeps the result alive.  bench.py times it with CUDA events to
+ * get the denominator of K2's roofline (MEASURED_PEAKS.json has no FP64 entry). */
+int icnn_fp64_mma_probe(int32_t iters, double* sink, double* flops_out, void* stream);
 
 #ifdef __cplusplus
 }

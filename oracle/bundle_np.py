@@ -37,7 +37,7 @@ def max_step(v, dv):
     return 1.0
 
 
-def pdipm_pc(G, h, dense_diag=False, stats=None):
+def pdipm_pc(G, h, dense_diag=False, stats=None, verbose=False):
     """Mehrotra predictor-corrector for
          min_{y in (0,1)^n, t}  t + sum y log y + (1-y) log(1-y)   s.t.  G y + h <= t 1
     (lib/bundle_entropy.py:5-78).  Returns (y, z) with z the multipliers (= lambda)."""
@@ -58,8 +58,15 @@ def pdipm_pc(G, h, dense_diag=False, stats=None):
             if stats is not None:
                 stats.append(it)
             return y, z
+        if verbose:   # the reference prints this line every iteration (lib/bundle_entropy.py:30-36)
+            d_ = z / s
+            print(("primal_res = {0:.5g}, dual_res = {1:.5g}, " + "gap = {2:.5g}, kappa(d) = {3:.5g}").format(
+                pri, dua, s.dot(z) / k, min(d_) / max(d_)))
         w = 1.0 / (1.0 / y + 1.0 / (1.0 - y))
         if dense_diag:
+            # the reference's cost model: BOTH dense n x n diagonal matrices are built every iteration
+            # (lib/bundle_entropy.py:17-18) and G.dot(hess_negH_inv) is a dense k x n x n product (:41,46)
+            hess_negH = np.diag(1.0 / y + 1.0 / (1.0 - y))   # noqa: F841  (built and unused, as in the reference)
             Dm = np.diag(w)
             GD = G.dot(Dm)
         else:
@@ -73,11 +80,14 @@ def pdipm_pc(G, h, dense_diag=False, stats=None):
         Minv1 = csolve(ones)
 
         def kkt(ry_, rt_, rc_, rd_):
-            r = rd_ - GD.dot(ry_) - (s / z) * rc_
+            if dense_diag:   # :46 recomputes G.dot(hess_negH_inv) in every solve, :50 multiplies by the dense matrix
+                r = rd_ - G.dot(Dm).dot(ry_) - (s / z) * rc_
+            else:
+                r = rd_ - GD.dot(ry_) - (s / z) * rc_
             dt = (r.dot(Minv1) - rt_) / Minv1.sum()
             dz = csolve(r - dt)
             ds = -(s / z) * (rc_ + dz)
-            dy = -w * (ry_ + G.T.dot(dz))
+            dy = -Dm.dot(ry_ + G.T.dot(dz)) if dense_diag else -w * (ry_ + G.T.dot(dz))
             return dt, dz, ds, dy
 
         dt_a, dz_a, ds_a, dy_a = kkt(ry, rt, rc, rd)
@@ -242,7 +252,7 @@ def proj_newton_logistic(A, b, rl=False, line_search=None, stats=None):
 
 
 def solve_batch(fg, initXs, nIter=None, callback=None, solver="pc", variant="lib",
-                dense_diag=False, line_search=None, stats=None):
+                dense_diag=False, line_search=None, stats=None, verbose=False):
     """The outer bundle loop shared by the three copies.
 
     variant 'lib'  -> lib/bundle_entropy.py:192-242   (PC / Boyd solve, prune lam <= 1e-8,
@@ -290,7 +300,7 @@ def solve_batch(fg, initXs, nIter=None, callback=None, solver="pc", variant="lib
             bu = np.array(b[u])
             if variant == "lib":
                 if solver == "pc":
-                    x[u], lam[u] = pdipm_pc(Au, bu, dense_diag=dense_diag, stats=stats)
+                    x[u], lam[u] = pdipm_pc(Au, bu, dense_diag=dense_diag, stats=stats, verbose=verbose)
                 else:
                     x[u], lam[u] = pdipm_boyd(Au, bu)
             else:
