@@ -351,7 +351,7 @@ def solveBatch(fg, initXs, nIter=None, callback=None, solver="pc", *, variant="l
     if isinstance(x0, np.ndarray) and x0.dtype == np.float64:
         x0[...] = x
         x = x0
-    nIters = [int(v) for v in st.nIters.cpu().numpy()]
+    nIters = st.nIters.cpu().numpy().tolist()     # a Python list like the reference's (ndarray.tolist: 65 536 rows in ~1 ms)
     st.status_host = status
     out = (x, _Rows(st, "A"), _Rows(st, "b"), _Rows(st, "lam"), _Rows(st, "xs"), nIters)
     if return_state:

@@ -41,6 +41,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok;
@@ -134,6 +137,7 @@ __device__ __forceinline__ float tf32_lo(float x, float hi) { return tf32_rn(x -
 // ---------------------------------------------------------------------------------------------
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;  // fp32 elements per stage row = one 128-byte swizzle span
+constexpr int TC_CH = 1;   // k-blocks per accumulation chunk (K = 32: four accumulations per TMEM accumulator before the RN drain)
 
 struct TcArgs {
   int M, N, K;
@@ -183,8 +187,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
   uint64_t* empty = full + SM::NST;
-  uint64_t* tmem_full = empty + SM::NST;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* acc_full = empty + SM::NST;     // [2] accumulator set s holds a finished chunk
+  uint64_t* acc_empty = acc_full + 2;       // [2] set s has been drained by the four epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
@@ -198,13 +203,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
     for (int s = 0; s < SM::NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // Four FP32 accumulators of BN columns each: the tensor core rounds its accumulator toward zero
-  // on every MMA, so one accumulator over K=2048 (768 sequential adds with the 3xTF32 split) drifts
-  // to ~2e-5 relative (measured).  The hi*hi products rotate over accumulators 0..2, the 2^-11
-  // smaller cross terms go to accumulator 3, and the epilogue adds the four in FP32 (RN).
+  // Chunked accumulation (round 2).  The tensor core truncates its FP32 accumulator toward zero at every MMA:
+  // a systematic relative bias of ~3e-8 per accumulation (tools/tc_bias_probe.py: -1.2e-5 at K = 5120 in one
+  // accumulator chain, -1.2e-6 with K cut into 640-slices, -1.7e-7 with 128-slices), which compounds through
+  // the layers (C5: f scaled by 1 - 1.1e-5) and moves y* by 3e-3 over 50 bundle iterations.  The reduction is
+  // therefore cut into CHUNKS of TC_CH k-blocks: the MMA warp accumulates one chunk in TMEM accumulator set
+  // (c & 1) -- hi*hi products in one accumulator, the 2^-11 smaller cross terms in a second -- while the four
+  // epilogue warps drain the other set into FP32 REGISTERS with round-to-nearest adds.  4 x BN TMEM columns as
+  // before (2 sets x 2 accumulators).
   if (warp == 1) tmem_alloc(tmem_slot, 4 * BN);
   tc_fence_before();
   __syncthreads();
@@ -230,29 +239,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % SM::NST;
-        const uint32_t ph = (kb / SM::NST) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * SM::STAGE_BYTES);
-        const uint64_t dAh = make_kmajor_sw128_desc(st);
-        const uint64_t dAl = make_kmajor_sw128_desc(st + SM::A_BYTES);
-        const uint64_t dBh = make_kmajor_sw128_desc(st + 2 * SM::A_BYTES);
-        const uint64_t dBl = make_kmajor_sw128_desc(st + 2 * SM::A_BYTES + SM::B_BYTES);
+      const int nch = (nkb + TC_CH - 1) / TC_CH;
+      for (int c = 0; c < nch; ++c) {
+        const int set = c & 1;
+        if (c >= 2) { mbar_wait(&acc_empty[set], (uint32_t)(((c >> 1) - 1) & 1)); tc_fence_after(); }
+        const uint32_t hh = tmem_base + (uint32_t)((2 * set) * BN);
+        const uint32_t xx = tmem_base + (uint32_t)((2 * set + 1) * BN);
+        const int kb1 = ::min(nkb, (c + 1) * TC_CH);
+        for (int kb = c * TC_CH; kb < kb1; ++kb) {
+          const int s = kb % SM::NST;
+          const uint32_t ph = (kb / SM::NST) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * SM::STAGE_BYTES);
+          const uint64_t dAh = make_kmajor_sw128_desc(st);
+          const uint64_t dAl = make_kmajor_sw128_desc(st + SM::A_BYTES);
+          const uint64_t dBh = make_kmajor_sw128_desc(st + 2 * SM::A_BYTES);
+          const uint64_t dBl = make_kmajor_sw128_desc(st + 2 * SM::A_BYTES + SM::B_BYTES);
 #pragma unroll
-        for (int k4 = 0; k4 < TC_BK / 8; ++k4) {
-          const uint64_t adv = (uint64_t)((k4 * 8 * 4) >> 4);  // +32 B per k-step inside the swizzle span
-          const int step = kb * (TC_BK / 8) + k4;
-          const uint32_t hh = tmem_base + (uint32_t)((step % 3) * BN);
-          const uint32_t xx = tmem_base + (uint32_t)(3 * BN);
-          umma_tf32(hh, dAh + adv, dBh + adv, idesc, step >= 3 ? 1u : 0u);
-          umma_tf32(xx, dAh + adv, dBl + adv, idesc, step ? 1u : 0u);
-          umma_tf32(xx, dAl + adv, dBh + adv, idesc, 1u);
+          for (int k4 = 0; k4 < TC_BK / 8; ++k4) {
+            const uint64_t adv = (uint64_t)((k4 * 8 * 4) >> 4);  // +32 B per k-step inside the swizzle span
+            const uint32_t first = (kb == c * TC_CH && k4 == 0) ? 0u : 1u;
+            umma_tf32(hh, dAh + adv, dBh + adv, idesc, first);
+            umma_tf32(xx, dAh + adv, dBl + adv, idesc, first);
+            umma_tf32(xx, dAl + adv, dBh + adv, idesc, 1u);
+          }
+          umma_commit(&empty[s]);  // stage free once these MMAs have read it
         }
-        umma_commit(&empty[s]);  // stage free once these MMAs have read it
+        umma_commit(&acc_full[set]);   // chunk complete in accumulator set `set`
       }
-      umma_commit(tmem_full);    // accumulator complete
     }
     __syncwarp();
   } else {
@@ -260,11 +275,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     // tcgen05.ld gives every thread one ROW of the tile; global traffic wants one row per WARP
     // instruction (lanes = consecutive columns).  Each epilogue warp transposes 32x32 chunks through
     // a padded tile carved out of the (now idle) stage-0 operand buffer.
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
     const int q = warp & 3;               // TMEM lane quarter this warp may access
+    // running sums of this thread's row (TMEM lane) in FP32 registers, round-to-nearest adds
+    float run[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) run[j] = 0.f;
+    {
+      const int nch = (nkb + TC_CH - 1) / TC_CH;
+      for (int c = 0; c < nch; ++c) {
+        const int set = c & 1;
+        mbar_wait(&acc_full[set], (uint32_t)((c >> 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32], w[32];
+          const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((2 * set) * BN + c0);
+          tmem_ld32(tb, v);          // hi*hi
+          tmem_ld32(tb + BN, w);     // cross terms
+#pragma unroll
+          for (int j = 0; j < 32; ++j) run[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(w[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[set]);
+      }
+    }
     float* tile = reinterpret_cast<float*>(smem) + q * (32 * 33);
-    const int nsteps = nkb * (TC_BK / 8);
     // bundle-slot row pointer of the row this lane would own (backward mode), broadcast by shuffle
     unsigned long long growp = 0;
     if (a.mode == 1) {
@@ -280,17 +316,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       // (every CTA of the cluster reaches both cluster barriers: warps 0/1 call them below)
       float* P = reinterpret_cast<float*>(smem);                  // [128][BN + 1] floats in the idle ring
       constexpr int PP = BN + 1;
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32], w[32];
-        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        if (nkb > 0) tmem_ld32(tb, v);
-        else { for (int j = 0; j < 32; ++j) v[j] = 0u; }
-        if (nsteps > 1) { tmem_ld32(tb + BN, w); for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j])); }
-        if (nsteps > 2) { tmem_ld32(tb + 2 * BN, w); for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j])); }
-        if (nkb > 0) { tmem_ld32(tb + 3 * BN, w); for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j])); }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) P[(q * 32 + lane) * PP + c0 + j] = __uint_as_float(v[j]);
-      }
+      for (int j = 0; j < BN; ++j) P[(q * 32 + lane) * PP + j] = run[j];
       tc_fence_before();
       cg::this_cluster().sync();
       cg::cluster_group cl = cg::this_cluster();
@@ -349,24 +376,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       }
       cg::this_cluster().sync();   // partial tiles stay alive until every rank has read them
     } else
+#pragma unroll
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= a.N) break;          // warp-uniform: whole chunk out of range
-      uint32_t v[32], w[32];
-      const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      tmem_ld32(tb, v);                                  // hi*hi accumulator 0 (always written)
-      if (nsteps > 1) {
-        tmem_ld32(tb + BN, w);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
-      }
-      if (nsteps > 2) {
-        tmem_ld32(tb + 2 * BN, w);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
-      }
-      tmem_ld32(tb + 3 * BN, w);                         // cross terms
-#pragma unroll
-      for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
+      for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = run[c0 + j];
       __syncwarp();
       const int nn = n0 + c0 + lane;                     // this lane's column for the whole chunk
       const bool nv = nn < a.N;
@@ -556,8 +570,32 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// Tensor maps are pure functions of (base, rows, cols, pitch, box): the weights of a handle and the workspace
+// operands of a bound minibatch see the same tuples on every iteration of every solveBatch, so the encoded
+// descriptors are kept in a small per-thread table instead of calling cuTensorMapEncodeTiled four times per GEMM
+// launch (480 encodes per C2 solveBatch).  Direct-mapped, 256 entries, overwritten on collision.
+struct TmapKey { const void* base; long long rows, cols, ld; int box; };
+struct TmapSlot { TmapKey k; CUtensorMap tm; bool valid; };
+static thread_local TmapSlot g_tmap_cache[256];
+
+static int make_tmap_uncached(CUtensorMap* tm, const float* base, long long rows, long long cols, long long ld, int box_rows);
+
 // 2-D fp32 tensor [rows, cols] (cols contiguous, row pitch ld floats), box = [box_rows, 32 cols], 128B swizzle
 static int make_tmap(CUtensorMap* tm, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+  unsigned long long hsh = reinterpret_cast<unsigned long long>(base) >> 6;
+  hsh ^= (unsigned long long)rows * 0x9E3779B97F4A7C15ull ^ (unsigned long long)cols * 0xC2B2AE3D27D4EB4Full ^
+         (unsigned long long)ld * 0x165667B19E3779F9ull ^ (unsigned long long)box_rows;
+  TmapSlot& sl = g_tmap_cache[(hsh ^ (hsh >> 17) ^ (hsh >> 31)) & 255];
+  if (sl.valid && sl.k.base == base && sl.k.rows == rows && sl.k.cols == cols && sl.k.ld == ld && sl.k.box == box_rows) {
+    *tm = sl.tm;
+    return ICNN_OK;
+  }
+  const int rc = make_tmap_uncached(tm, base, rows, cols, ld, box_rows);
+  if (rc == ICNN_OK) { sl.k = TmapKey{base, rows, cols, ld, box_rows}; sl.tm = *tm; sl.valid = true; }
+  return rc;
+}
+
+static int make_tmap_uncached(CUtensorMap* tm, const float* base, long long rows, long long cols, long long ld, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ICNN_E_CUDA; }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -602,9 +640,17 @@ static int launch_tc_gemm(const float* Ah, const float* Al, long long lda, const
   // (measured on B200, T shape: 64x2 4.28 ms, 128 5.12 ms, 64x4 6.62 ms per 10 iterations of K1;
   //  C2, 28 tiles: 64x4 7.5 ms, 64x2 8.0 ms, 128 9.2 ms)
   int cfg = (cdiv(a.N, 64) * gy >= 296) ? 2 : 1;
-  if (const char* v = getenv("ICNN_TC_CFG")) {
-    if (!strcmp(v, "128")) cfg = 0; else if (!strcmp(v, "64x4")) cfg = 1; else if (!strcmp(v, "64x2")) cfg = 2;
-  }
+  static const int env_cfg = [] {     // tuning knobs are read once per process, not per launch
+    const char* v = getenv("ICNN_TC_CFG");
+    if (!v) return -1;
+    return !strcmp(v, "128") ? 0 : !strcmp(v, "64x4") ? 1 : !strcmp(v, "64x2") ? 2 : -1;
+  }();
+  static const int env_splitk = [] {
+    const char* v = getenv("ICNN_TC_SPLITK");
+    const int w = v ? atoi(v) : 0;
+    return (w == 1 || w == 2 || w == 4 || w == 8) ? w : 0;
+  }();
+  if (env_cfg >= 0) cfg = env_cfg;
   if (gdb && cfg == 0) cfg = 1;
   const int BN = cfg == 0 ? 128 : 64;
   CUtensorMap tAh, tAl, tBh, tBl;
@@ -618,7 +664,7 @@ static int launch_tc_gemm(const float* Ah, const float* Al, long long lda, const
   if (cfg == 1 && (a.mode == 0 || a.mode == 1)) {
     const int tiles = cdiv(a.N, 64) * gy, nkb = cdiv(a.K, TC_BK);
     while (splitk < 8 && tiles * splitk * 2 <= 148 && nkb / (splitk * 2) >= 4) splitk *= 2;
-    if (const char* v = getenv("ICNN_TC_SPLITK")) { const int w = atoi(v); if (w == 1 || w == 2 || w == 4 || w == 8) splitk = w; }
+    if (env_splitk) splitk = env_splitk;
   }
   cudaError_t e;
   if (gdb)   // GD training backward: the 64-wide variants with the tangent / accumulation epilogue

@@ -75,7 +75,12 @@ class PICNN:
 
     @classmethod
     def from_params(cls, p, device=None):
-        """Build from any object with the attribute names of oracle/picnn_np.PicnnParams."""
+        """Build from any object with the attribute names of oracle/picnn_np.PicnnParams.  An inference-mode
+        batch-norm on the u-path (``p.bn``, multi-label-cls/icnn_ebundle.py:343-345) is folded into the
+        weights of its consumers (workloads.fold_batchnorm): the handle then holds the folded x-path weights."""
+        if any(b is not None for b in getattr(p, "bn", []) or []):
+            from .workloads import fold_batchnorm
+            p = fold_batchnorm(p)
         return cls(p.m, p.n, p.hidden, p.Wy, p.Wz, p.Wu, p.bu, p.Wzu, p.bzu, p.Wyu, p.byu, p.Wzx,
                    p.bzx, alpha=p.alpha, device=device)
 

@@ -25,6 +25,10 @@ class PicnnParams:
       Wzx[i], bzx[i] : d_i  =      P_i @ Wzx[i] + bzx[i]    in R^{s_i}
       with P_0 = x, P_i = u_{i-1}.
     alpha : leaky-ReLU slope on the z path (0 -> ReLU, multi-label; 0.01 RL).
+    bn[i] : optional inference-mode batch-norm after the ReLU of u_i, i < L-1
+            (multi-label-cls/icnn_ebundle.py:343-345, RL/src/icnn.py:348-351 with --icnn_bn), given as the
+            per-feature affine map it is at inference time: ``(scale, shift)`` with
+            scale = gamma / sqrt(moving_var + eps), shift = beta - moving_mean * scale  (``bn_affine``).
     """
 
     def __init__(self, m, n, hidden, alpha=0.0):
@@ -38,10 +42,37 @@ class PicnnParams:
         self.Wzu, self.bzu = [None] * (L + 1), [None] * (L + 1)
         self.Wyu, self.byu = [None] * (L + 1), [None] * (L + 1)
         self.Wzx, self.bzx = [None] * (L + 1), [None] * (L + 1)
+        self.bn = [None] * L
 
     def prev_width(self, i):
         """Width of P_i (the x-path activation feeding layer i's gates)."""
         return self.m if i == 0 else self.hidden[i - 1]
+
+
+def bn_affine(gamma, beta, moving_mean, moving_var, eps=1e-5):
+    """Inference-mode batch normalisation as a per-feature affine map (tflearn batch_normalization with
+    is_training = False: (x - mean) / sqrt(var + eps) * gamma + beta).  eps: tflearn's default is 1e-5."""
+    scale = np.asarray(gamma, dtype=np.float64) / np.sqrt(np.asarray(moving_var, dtype=np.float64) + eps)
+    return scale, np.asarray(beta, dtype=np.float64) - np.asarray(moving_mean, dtype=np.float64) * scale
+
+
+def fold_batchnorm(p):
+    """Fold the inference-mode batch-norm of the u-path into the weights of its consumers and return a copy
+    WITHOUT bn:  u_i = s o r + t (r = relu(fc)) feeds u_{i+1} and the three gate layers of z-layer i+1 as
+    P W + b, and (s o r + t) W + b = r (diag(s) W) + (b + t W).  Exact in real arithmetic; this is how the
+    device path honours BN (the x-path GEMM epilogue stays bias + ReLU)."""
+    import copy
+    q = copy.deepcopy(p)
+    for i in range(p.L - 1):
+        if p.bn[i] is None:
+            continue
+        s_, t_ = (np.asarray(v, dtype=np.float64) for v in p.bn[i])
+        for W, b in ((q.Wu, q.bu), (q.Wzu, q.bzu), (q.Wyu, q.byu), (q.Wzx, q.bzx)):
+            W0 = np.asarray(W[i + 1], dtype=np.float64)
+            b[i + 1] = np.asarray(b[i + 1], dtype=np.float64) + t_ @ W0
+            W[i + 1] = s_[:, None] * W0
+        q.bn[i] = None
+    return q
 
 
 def synth_params(seed, m, n, hidden, alpha=0.0, gate_bias=0.0, dtype=np.float32):

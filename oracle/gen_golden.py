@@ -52,6 +52,10 @@ CASES = [
     ("t_dual", "T", 8, 10, "dual", None),
     ("c2_pc", "C2", 4, 30, "lib", "pc"),
     ("c5_pc", "C5", 2, 8, "lib", "pc"),
+    # round 2: the configs' OWN horizons -- KS = 51 at C5, 30 iterations at C2
+    ("c3_pc_full", "C3", 32, 10, "lib", "pc"),
+    ("c2_pc_full", "C2", 8, 30, "lib", "pc"),
+    ("c5_pc_full", "C5", 2, 50, "lib", "pc"),
 ]
 
 

@@ -27,9 +27,9 @@ from icnn_b200.workloads import PicnnParams, synth_params  # noqa: E402,F401  (d
 
 def gates(p: PicnnParams, x):
     """x-path: returns (cz, cy, d) lists indexed by z-layer (cz[0] is None).
-    multi-label-cls/icnn_ebundle.py:339-347 (u path; batch-norm is treated as caller-supplied,
-    i.e. identity here -- tflearn BN defaults are un-pinned),
-    :354-356 (cz), :363-365 (cy), :372-373 (d)."""
+    multi-label-cls/icnn_ebundle.py:339-347 (u path; inference-mode batch-norm after the ReLU when
+    ``p.bn[i]`` is given, as the per-feature affine map (scale, shift) -- tflearn's epsilon / moving
+    averages are the caller's), :354-356 (cz), :363-365 (cy), :372-373 (d)."""
     x = np.asarray(x, dtype=np.float64)
     L = p.L
     us = []
@@ -38,6 +38,9 @@ def gates(p: PicnnParams, x):
         u = prev @ p.Wu[i] + p.bu[i]
         if i < L - 1:
             u = np.maximum(u, 0.0)
+            bn = getattr(p, "bn", None)
+            if bn is not None and bn[i] is not None:     # :343-345  u = bn(relu(fc(prevU)))
+                u = u * np.asarray(bn[i][0], dtype=np.float64) + np.asarray(bn[i][1], dtype=np.float64)
         us.append(u)
         prev = u
     cz, cy, d = [None] * (L + 1), [None] * (L + 1), [None] * (L + 1)

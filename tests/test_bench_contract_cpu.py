@@ -27,6 +27,23 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] and "workload" in d["config"]
+    # the reference arm maps no native code: icnn_b200's package init is lazy and bench.py only touches
+    # icnn_b200.workloads (pure numpy) on this arm (measurement hygiene 7)
+    assert d["native_modules_loaded"] == []
+    assert d["config"]["workload"].startswith("C1: ") and "/GPU" not in d["config"]["workload"]
+
+
+def test_workloads_import_does_not_load_the_native_library():
+    code = ("import sys; from icnn_b200 import workloads; "
+            "assert 'icnn_b200._capi' not in sys.modules and 'torch' not in sys.modules; print('ok')")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-1000:]
+
+
+def test_default_workload_is_the_largest_single_gpu_config():
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert 'ap.add_argument("--workload", default="C5"' in src
+    assert 'scaling = args.scaling or "strong"' in src
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -44,7 +44,7 @@ def _worker(rank, ws, port, B, n, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ws,B", [(2, 8), (2, 7), (3, 10)])
+@pytest.mark.parametrize("ws,B", [(2, 8), (2, 7), (3, 10), (3, 2), (2, 1)])   # B < ws: a rank with NO rows still gathers
 def test_allgather_rows_gloo(ws, B):
     port = _free_port()
     ctx = mp.get_context("spawn")

@@ -23,6 +23,30 @@ pytestmark = pytest.mark.gpu
 np.seterr(all="ignore")
 
 
+def _parity_record(key, d, floor, extra=None):
+    """Append the per-config parity statistics to gpurun_out/r02_parity_raw.json (copied to
+    profiles/r02_parity.json by hand after a GPU run; a missing directory is not an error)."""
+    import json
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if not os.path.isdir(out):
+        return
+    path = os.path.join(out, "r02_parity_raw.json")
+    try:
+        with open(path) as f:
+            data = json.load(f)
+    except Exception:
+        data = {}
+    rec = {"rows": int(d.size), "device_vs_ref": {"max": float(d.max()), "median": float(np.median(d)),
+                                                  "frac_gt_1e-4": float(np.mean(d > 1e-4))},
+           "oracle_f32_floor": {"max": float(floor.max()), "median": float(np.median(floor)),
+                                "frac_gt_1e-4": float(np.mean(floor > 1e-4))}}
+    if extra:
+        rec.update(extra)
+    data[key] = rec
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1, sort_keys=True)
+
+
 def r32(fg):
     def w(y):
         f, g = fg(y)
@@ -103,7 +127,9 @@ def test_k2_rl_matches_oracle(B, nIter):
 GOLD = [("c1_pc", 1e-5, 1e-7), ("c1_dual", 1e-5, 1e-7), ("c1_rl", None, 1e-6), ("c1_boyd", None, None),
         ("c1_pc_long", 1e-5, 1e-7), ("c3_pc", None, 1e-5), ("c3_dual", None, 1e-5), ("c4_rl", 1e-5, 1e-6),
         ("c4_rl_long", 1e-4, 1e-6), ("t_pc", 1e-4, 1e-5), ("t_dual", 1e-4, 1e-5), ("c2_pc", "long", 1e-3),
-        ("c5_pc", 1e-4, 1e-5)]
+        ("c5_pc", 1e-4, 1e-5),
+        # round 2: the configs' own horizons, judged against the oracle's float32 noise floor measured in the test
+        ("c3_pc_full", "floor", None), ("c2_pc_full", "floor", None), ("c5_pc_full", "floor", None)]
 
 
 @pytest.mark.parametrize("case,maxtol,medtol", GOLD)
@@ -126,6 +152,23 @@ def test_k2_against_reference_golden(case, maxtol, medtol, golden_dir):
         # iterations stop short of the optimum, so only closeness of the objective is asked
         fgv = lambda y: fg(y)[0] + np.sum(y * np.log(y) + (1 - y) * np.log(1 - y), axis=1)  # noqa: E731
         assert np.all(fgv(r[0]) <= fgv(gold["x"]) + 1e-6)
+        return
+    if maxtol == "floor":
+        # Long horizons: the float64 reference itself moves when (f, g) are rounded to float32 (the iterates
+        # converge onto ReLU kinks).  Measure that floor here -- the oracle fed the float32-rounded fg against the
+        # reference's golden y* -- and require the device to stay within it: fraction of samples off by more
+        # than 1e-4 <= floor + 0.02 (one sample of 32 is 0.03: + 1 sample), median <= max(1e-6, 4 x floor median).
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            o32 = bundle_np.solve_batch(r32(fg), y0.copy(), nIter=nIter, variant=variant)
+        fl = rowdiff(o32[0], gold["x"])
+        print("\n%s: device-vs-reference max %.2e median %.2e frac>1e-4 %.3f | oracle(f32 fg)-vs-reference max %.2e "
+              "median %.2e frac>1e-4 %.3f" % (case, d.max(), np.median(d), np.mean(d > 1e-4), fl.max(), np.median(fl),
+                                              np.mean(fl > 1e-4)))
+        _parity_record(case, d, fl)
+        assert np.mean(d > 1e-4) <= np.mean(fl > 1e-4) + max(0.02, 1.0 / B + 1e-9), (np.mean(d > 1e-4), np.mean(fl > 1e-4))
+        assert np.median(d) <= max(1e-6, 4 * np.median(fl)), (np.median(d), np.median(fl))
+        assert d.max() <= max(1e-4, 10 * fl.max()), (d.max(), fl.max())
         return
     if maxtol == "long":
         # 30 iterations at n=2048: the float64 oracle itself moves by up to 1e-3 under float32
@@ -171,7 +214,8 @@ def test_fused_vs_oracle(name, B, nIter, maxtol):
         assert d.max() < maxtol
     else:
         assert np.median(d) < max(1e-5, 4 * np.median(floor))
-        assert np.mean(d > 1e-4) <= np.mean(floor > 1e-4) + 0.1
+        _parity_record("fused_%s_B%d_it%d" % (name, B, nIter), d, floor)
+        assert np.mean(d > 1e-4) <= np.mean(floor > 1e-4) + max(0.02, 1.0 / B + 1e-9)
     # objective gap: f - H at the GPU solution is as good as the oracle's
     fg64 = picnn_np.make_fg(p, x, affine=cfg["affine"])
     obj = lambda y: fg64(y)[0] + np.sum(y * np.log(y) + (1 - y) * np.log(1 - y), axis=1)  # noqa: E731
@@ -256,6 +300,49 @@ def test_fused_properties_at_full_size_other_configs(name):
         assert np.all(Gu.dot(y[u]) + np.array(h[u]) <= f_star[u] + 1e-3 * max(1, abs(f_star[u])))
 
 
+FULLSIZE = [("C3", 64), ("T", 64), ("C4", 64), ("C2", 48), ("C5", 12)]
+
+
+@pytest.mark.parametrize("name,nsub", FULLSIZE)
+def test_full_size_subsample_matches_oracle(name, nsub):
+    """BASELINE.json's configs at FULL size and FULL horizon (C5: 8192 x 4096, 50 iterations, 51 slots): the
+    samples are independent (lib/bundle_entropy.py:211), so a random subsample of the device result is compared
+    with the float64 oracle run on exactly those rows, next to the oracle's own float32 noise floor on the same
+    rows.  Tolerance: fraction of rows off by more than 1e-4 <= floor + 0.02 (+ one row), median <=
+    max(1e-5, 4 x floor median); at the short horizons (C3 / C4 / T) the floor is ~0 and this is the 1e-4 statement."""
+    import icnn_b200
+    from icnn_b200 import bundle_entropy as be
+    cfg = synth.CONFIGS[name]
+    p, x, y0 = synth.make_inputs(name)
+    B, nIter, variant = cfg["B"], cfg["nIter"], cfg["variant"]
+    net = icnn_b200.PICNN.from_params(p)
+    r = be.solveBatch(net.bind(x, affine=cfg["affine"]), y0.copy(), nIter=nIter, variant=variant)
+    rows = np.sort(np.random.RandomState(7).choice(B, size=nsub, replace=False))
+    xs, ys = x[rows], y0[rows]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = bundle_np.solve_batch(picnn_np.make_fg(p, xs, affine=cfg["affine"]), ys.copy(), nIter=nIter, variant=variant)
+        o32 = bundle_np.solve_batch(picnn_np.make_fg(p, xs, affine=cfg["affine"], dtype=np.float32, out_dtype=np.float64),
+                                    ys.copy(), nIter=nIter, variant=variant)
+    d = rowdiff(r[0][rows], o[0])
+    floor = rowdiff(o32[0], o[0])
+    kdev = lens([r[1][int(u)] for u in rows])
+    print("\n%s full size, %d-row subsample: device-vs-oracle max %.2e median %.2e frac>1e-4 %.3f | oracle f32 floor max "
+          "%.2e median %.2e frac>1e-4 %.3f | active rows device mean %.1f oracle mean %.1f"
+          % (name, nsub, d.max(), np.median(d), np.mean(d > 1e-4), floor.max(), np.median(floor), np.mean(floor > 1e-4),
+             kdev.mean(), lens(o[1]).mean()))
+    _parity_record("fullsize_%s" % name, d, floor, {"B": B, "nIter": nIter, "KS": (nIter if variant == "rl" else min(nIter, cfg["n"])) + 1,
+                                                   "active_rows_device_mean": float(kdev.mean()),
+                                                   "active_rows_oracle_mean": float(lens(o[1]).mean())})
+    assert np.mean(d > 1e-4) <= np.mean(floor > 1e-4) + 0.02 + 1.0 / nsub, (np.mean(d > 1e-4), np.mean(floor > 1e-4))
+    assert np.median(d) <= max(1e-5, 4 * np.median(floor)), (np.median(d), np.median(floor))
+    # objective: f - H at the device solution is as good as the oracle's on those rows
+    fg64 = picnn_np.make_fg(p, xs, affine=cfg["affine"])
+    obj = lambda y: fg64(y)[0] + np.sum(y * np.log(y) + (1 - y) * np.log(1 - y), axis=1)  # noqa: E731
+    gap = (obj(r[0][rows]) - obj(o[0])) / np.maximum(1.0, np.abs(obj(o[0])))
+    assert np.median(np.abs(gap)) < 1e-5 and gap.max() < 1e-3, gap
+
+
 def test_edge_cases_and_error_paths():
     import icnn_b200
     from icnn_b200 import bundle_entropy as be
@@ -290,6 +377,43 @@ def test_edge_cases_and_error_paths():
     assert rb[-1].status_host[3] == 4 and np.all(np.isfinite(rb[0][[0, 1, 2, 4]]))
     with pytest.raises(RuntimeError):
         be.solveBatch(bad, y0.copy(), nIter=3, strict=True)
+
+
+def test_slot_cap_float64_callback_stats_and_state_reuse():
+    """Round-2 API surface: the 64-slot cap is reported up front; a float64 fg keeps its f in float64 for the cut
+    offsets (the reference forms b = f - sum(g x) in float64, lib/bundle_entropy.py:205-207); per-iteration
+    statistics; a reused BundleState reproduces the result bit for bit."""
+    import icnn_b200
+    from icnn_b200 import bundle_entropy as be
+    p, x, y0 = synth.make_inputs("C3", B=40)
+    fg64 = picnn_np.make_fg(p, x)
+    # nIter > 63 with n_y >= 64: min(nIter, n) + 1 > 64 slots -> clear error instead of a launch failure
+    with pytest.raises(ValueError, match="64"):
+        be.solveBatch(fg64, y0.copy(), nIter=70)
+    # float64 f with bits below float32 resolution, float32-representable rows: the offsets must follow the float64 f
+    def fg_f64(y):
+        f, g = fg64(y)
+        return f + 1e-9 * np.arange(1, len(f) + 1), g.astype(np.float32).astype(np.float64)
+    o = bundle_np.solve_batch(fg_f64, y0.copy(), nIter=4)
+    r = be.solveBatch(fg_f64, y0.copy(), nIter=4)
+    for u in (0, 7, 39):
+        np.testing.assert_allclose(np.array(r[2][u]), np.array(o[2][u]), rtol=0, atol=1e-11)   # h = f - g.y from the f64 f
+    assert rowdiff(r[0], o[0]).max() < 1e-9
+    # per-iteration statistics + state reuse on the fused path
+    net = icnn_b200.PICNN.from_params(p)
+    fgd = net.bind(x)
+    seen = []
+    r1 = be.solveBatch(fgd, y0.copy(), nIter=6, return_state=True, stats=True,
+                       callback=lambda t, f, xx: seen.append(float(np.mean(f + np.sum(xx * np.log(xx) + (1 - xx) * np.log(1 - xx), axis=1)))))
+    st = r1[-1]
+    sd = st.stats()
+    assert sd["entering"][0] == 40 and np.all(np.diff(sd["entering"]) <= 0)
+    np.testing.assert_allclose(sd["mean_f_minus_H"][:len(seen)][sd["entering"][:len(seen)] == 40],
+                               np.array(seen)[sd["entering"][:len(seen)] == 40], rtol=1e-5, atol=1e-4)
+    assert np.all(sd["inner_its"][:len(seen)] >= sd["entering"][:len(seen)] - sd["stopped"][:len(seen)])
+    ya = be.solveBatch(fgd, y0.copy(), nIter=6)[0]
+    yb = be.solveBatch(fgd, y0.copy(), nIter=6, state=st)[0]          # reused buffers, no allocation
+    assert np.array_equal(ya, yb)
 
 
 def test_early_exit_when_all_finished():

@@ -36,6 +36,22 @@ def test_fg_matches_oracle(name, B):
     assert np.abs(g - go).max() <= tol * max(1.0, np.abs(go).max())
 
 
+def test_long_reductions_carry_no_systematic_bias():
+    """C5 dims (K up to 5120 per GEMM, four hidden layers): the tensor core truncates its FP32 accumulator at
+    every MMA; uncorrected that is a systematic -2e-5 relative scaling of f and g which moves y* by 3e-3 at the
+    full C5 size.  With the chunked accumulation (TMEM chunk -> FP32 registers, RN) the SIGNED mean relative error of f must be ~0 and the
+    max error at the FP32-GEMM level.  (Fix: chunked accumulation, icnn_b200/csrc/picnn_tc.cu.)"""
+    cfg, p, x, y0, net = _net("C5", 256)
+    y = np.random.RandomState(12).uniform(0.02, 0.98, size=y0.shape).astype(np.float32).astype(np.float64)
+    f, g = net.bind(x)(y)
+    fo, go = picnn_np.make_fg(p, x)(y)
+    rel = (f - fo) / np.maximum(np.abs(fo), 1.0)
+    print("\nC5 f: signed mean rel err %.2e  max |rel err| %.2e ; g max err / max|g| %.2e"
+          % (rel.mean(), np.abs(rel).max(), np.abs(g - go).max() / np.abs(go).max()))
+    assert abs(rel.mean()) < 2e-6 and np.abs(rel).max() < 1e-5
+    assert np.abs(g - go).max() <= 1e-5 * np.abs(go).max()
+
+
 def test_fg_is_row_independent():
     """A row's result does not depend on which other rows share its batch, up to float32
     summation order (the split-K factor of the GEMM follows the grid size)."""
@@ -84,6 +100,37 @@ def test_xpath_gates_kernel_matches_oracle(name, B):
             g = got.cpu().numpy().astype(np.float64)
             assert g.shape == want.shape
             assert np.abs(g - want).max() <= 1e-5 * max(1.0, np.abs(want).max())
+
+
+def test_xpath_batchnorm_is_folded_into_the_gate_gemms():
+    """Inference-mode batch-norm on the u-path (multi-label-cls/icnn_ebundle.py:343-345; RL/src/icnn.py:350 with
+    --icnn_bn): PICNN.from_params folds the per-feature affine map into the consumer weights; the device gates
+    must equal the float64 oracle that applies u = bn(relu(fc(.))) literally."""
+    import icnn_b200
+    from icnn_b200 import workloads
+    p = workloads.synth_params(23, 64, 48, [96, 80, 64])
+    rs = np.random.RandomState(4)
+    for i in range(p.L - 1):
+        w = p.hidden[i]
+        p.bn[i] = workloads.bn_affine(rs.uniform(0.5, 1.5, w), 0.1 * rs.randn(w), 0.2 * rs.randn(w), rs.uniform(0.5, 2.0, w))
+    x = rs.randn(256, 64).astype(np.float32).astype(np.float64)
+    net = icnn_b200.PICNN.from_params(p)
+    cz, cy, d = net.gates(x)
+    ocz, ocy, od = picnn_np.gates(p, x)
+    nobn = picnn_np.gates(workloads.synth_params(23, 64, 48, [96, 80, 64]), x)
+    assert np.abs(ocy[2] - nobn[1][2]).max() > 1e-2          # the batch-norm matters in this case
+    for i in range(p.L + 1):
+        for got, want in ((cz[i], ocz[i]), (cy[i], ocy[i]), (d[i], od[i])):
+            if want is not None:
+                assert np.abs(got.cpu().numpy().astype(np.float64) - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
+    # and through the fused loop: same y* as the oracle that applies BN
+    from icnn_b200 import bundle_entropy as be
+    from oracle import bundle_np
+    y0 = np.full((256, 48), 0.5)
+    with np.errstate(all="ignore"):
+        o = bundle_np.solve_batch(picnn_np.make_fg(p, x), y0.copy(), nIter=5)
+    r = be.solveBatch(net.bind(x), y0.copy(), nIter=5)
+    assert np.abs(r[0] - o[0]).max() < 1e-4
 
 
 def test_xpath_falls_back_without_the_tensor_core_path(monkeypatch):

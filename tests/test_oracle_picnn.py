@@ -91,3 +91,27 @@ def test_momentum_gd_recurrence():
         yi = yi - 0.3 * prev + 1.3 * vi
     np.testing.assert_allclose(y, yi, atol=1e-14)
     np.testing.assert_allclose(f, fg(yi)[0], atol=1e-14)
+
+
+def test_batchnorm_fold_is_exact_in_float64():
+    """Inference-mode batch-norm on the u-path (multi-label-cls/icnn_ebundle.py:343-345) folded into the
+    consumer weights (icnn_b200.workloads.fold_batchnorm -- what the device path does) gives the same gates."""
+    from icnn_b200 import workloads
+    from oracle import picnn_np
+    p = workloads.synth_params(11, 20, 12, [24, 16, 10])
+    rs = np.random.RandomState(3)
+    for i in range(p.L - 1):
+        w = p.hidden[i]
+        p.bn[i] = workloads.bn_affine(rs.uniform(0.5, 1.5, w), rs.randn(w) * 0.1, rs.randn(w) * 0.2, rs.uniform(0.5, 2.0, w))
+    x = rs.randn(7, 20)
+    q = workloads.fold_batchnorm(p)
+    assert all(b is None for b in q.bn)
+    ga, gb = picnn_np.gates(p, x), picnn_np.gates(q, x)
+    for la, lb in zip(ga, gb):
+        for a, b in zip(la, lb):
+            if a is not None:
+                np.testing.assert_allclose(a, b, rtol=0, atol=1e-12)
+    # and BN really changes the gates (the test is not vacuous)
+    p0 = workloads.fold_batchnorm(p)
+    p0.Wu, p0.bu = p.Wu, p.bu
+    assert np.abs(picnn_np.gates(p, x)[1][1] - picnn_np.gates(workloads.synth_params(11, 20, 12, [24, 16, 10]), x)[1][1]).max() > 1e-3

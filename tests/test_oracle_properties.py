@@ -35,3 +35,20 @@ def test_subproblem_invariants(gh):
     assert abs(primal - dual) < 1e-6 * max(1.0, abs(primal))                 # strong duality
     if k == 1:
         np.testing.assert_allclose(yd, 1.0 / (1.0 + np.exp(G[0])), atol=1e-12)   # one cut: y = sigma(-g)
+
+
+def test_reference_cost_mode_is_the_same_algorithm():
+    """bench.py's `cpu_baseline.reference_cost` runs the port with the reference's dense np.diag matrices and
+    per-iteration prints (lib/bundle_entropy.py:17-18,34-36,41): same numbers, only slower."""
+    import contextlib
+    import io
+    from oracle import bundle_np, picnn_np, synth
+    p, x, y0 = synth.make_inputs("C1", B=6)
+    fg = picnn_np.make_fg(p, x)
+    with np.errstate(all="ignore"):
+        a = bundle_np.solve_batch(fg, y0.copy(), nIter=4)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            b = bundle_np.solve_batch(fg, y0.copy(), nIter=4, dense_diag=True, verbose=True)
+    np.testing.assert_allclose(a[0], b[0], atol=1e-10)
+    assert "primal_res" in buf.getvalue() and "kappa(d)" in buf.getvalue()
