@@ -107,7 +107,9 @@ def _xpath_backward(net, x, dcy, dcz):
 
 def make_cvx(Wz, halve=False):
     """``makeCvx``: W <- |W| (multi-label-cls/icnn-back.py:143), |W|/2 with ``halve``
-    (completion/icnn.back.py:164), for every 'proj' weight Wz[1..L]; in place on torch tensors."""
+    (completion/icnn.back.py:164), for every 'proj' weight Wz[1..L]; in place on torch tensors.
+    When applied to a PICNN's own tensors (``make_cvx(net.Wz)``) follow with ``net.update_weights()``: the
+    device library works on packed copies, and ``net.bind`` refuses to run on stale ones."""
     for w in Wz:
         if w is not None:
             w.abs_()
@@ -117,7 +119,7 @@ def make_cvx(Wz, halve=False):
 
 
 def proj(Wz):
-    """``proj``: W <- max(W, 0) (multi-label-cls/icnn-back.py:144)."""
+    """``proj``: W <- max(W, 0) (multi-label-cls/icnn-back.py:144).  Same re-packing rule as ``make_cvx``."""
     for w in Wz:
         if w is not None:
             w.clamp_(min=0)

@@ -51,6 +51,19 @@ class PICNN:
         self.Wzx = [_dev(w, d) for w in Wzx]
         self.bzx = [_dev(w, d) for w in bzx]
         assert len(self.Wy) == L + 1 and len(self.Wz) == L + 1
+        self._h = None
+        self._pack()
+
+    def _weight_tensors(self):
+        return [t for lst in (self.Wy, self.Wz, self.Wu, self.bu, self.Wzu, self.bzu, self.Wyu, self.byu, self.Wzx, self.bzx)
+                for t in lst if t is not None]
+
+    def _pack(self):
+        """Hand the current weight tensors to the C library (it keeps its own packed / TF32-split copies)."""
+        L = self.L
+        if self._h is not None and self._h.value:
+            _capi.lib.icnn_picnn_destroy(self._h)
+            self._h = None
         hid = (C.c_int32 * L)(*self.hidden)
         wy = _capi.ptr_array(self.Wy)
         wz = _capi.ptr_array(self.Wz)
@@ -72,6 +85,19 @@ class PICNN:
                 self._xpath = True
             elif rc != -3:           # -3 = ICNN_E_UNSUPPORTED (width not a multiple of 4 / SIMT-only build)
                 _capi.check(rc)
+        self._versions = [t._version for t in self._weight_tensors()]
+
+    def update_weights(self):
+        """Re-pack after the weight tensors were modified in place (an optimiser step, makeCvx / proj:
+        multi-label-cls/icnn_ebundle.py:140-144).  The library works on its own packed copies, so without this
+        call K1 / the gate GEMMs would keep using the old values; ``bind`` refuses to run on stale copies."""
+        with torch.cuda.device(self.device):
+            self._pack()
+
+    def _check_fresh(self):
+        if [t._version for t in self._weight_tensors()] != self._versions:
+            raise RuntimeError("PICNN: a weight tensor was modified in place after it was packed for the device "
+                               "library; call net.update_weights() before bind()")
 
     @classmethod
     def from_params(cls, p, device=None):
@@ -136,6 +162,7 @@ class PICNN:
     def bind(self, x, affine=False):
         """fg object for a minibatch x [B, m].  ``affine=True`` = the RL wrapper
         (RL/src/icnn.py:148-153): solver variable in [0,1], action a = 2x-1, gradient * 2."""
+        self._check_fresh()
         return BoundPICNN(self, x, affine)
 
 

@@ -157,7 +157,7 @@ def test_k2_against_reference_golden(case, maxtol, medtol, golden_dir):
         # Long horizons: the float64 reference itself moves when (f, g) are rounded to float32 (the iterates
         # converge onto ReLU kinks).  Measure that floor here -- the oracle fed the float32-rounded fg against the
         # reference's golden y* -- and require the device to stay within it: fraction of samples off by more
-        # than 1e-4 <= floor + 0.02 (one sample of 32 is 0.03: + 1 sample), median <= max(1e-6, 4 x floor median).
+        # than 1e-4 <= floor + max(0.02, 2.5 rows), median <= max(1e-6, 4 x floor median).
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             o32 = bundle_np.solve_batch(r32(fg), y0.copy(), nIter=nIter, variant=variant)
@@ -166,7 +166,7 @@ def test_k2_against_reference_golden(case, maxtol, medtol, golden_dir):
               "median %.2e frac>1e-4 %.3f" % (case, d.max(), np.median(d), np.mean(d > 1e-4), fl.max(), np.median(fl),
                                               np.mean(fl > 1e-4)))
         _parity_record(case, d, fl)
-        assert np.mean(d > 1e-4) <= np.mean(fl > 1e-4) + max(0.02, 1.0 / B + 1e-9), (np.mean(d > 1e-4), np.mean(fl > 1e-4))
+        assert np.mean(d > 1e-4) <= np.mean(fl > 1e-4) + max(0.02, 2.5 / B), (np.mean(d > 1e-4), np.mean(fl > 1e-4))
         assert np.median(d) <= max(1e-6, 4 * np.median(fl)), (np.median(d), np.median(fl))
         assert d.max() <= max(1e-4, 10 * fl.max()), (d.max(), fl.max())
         return
@@ -215,7 +215,9 @@ def test_fused_vs_oracle(name, B, nIter, maxtol):
     else:
         assert np.median(d) < max(1e-5, 4 * np.median(floor))
         _parity_record("fused_%s_B%d_it%d" % (name, B, nIter), d, floor)
-        assert np.mean(d > 1e-4) <= np.mean(floor > 1e-4) + max(0.02, 1.0 / B + 1e-9)
+        # floor + 0.02, or + 2.5 rows when the batch is small: device and float32 oracle are two independent float32
+        # realisations, the count of kink-flipped rows fluctuates by ~sqrt(count) between them
+        assert np.mean(d > 1e-4) <= np.mean(floor > 1e-4) + max(0.02, 2.5 / B)
     # objective gap: f - H at the GPU solution is as good as the oracle's
     fg64 = picnn_np.make_fg(p, x, affine=cfg["affine"])
     obj = lambda y: fg64(y)[0] + np.sum(y * np.log(y) + (1 - y) * np.log(1 - y), axis=1)  # noqa: E731
@@ -223,20 +225,25 @@ def test_fused_vs_oracle(name, B, nIter, maxtol):
     assert np.median(np.abs(gap)) < 1e-5 and gap.max() < 1e-3, gap
 
 
-def test_shard_concat_equals_unsharded():
+@pytest.mark.parametrize("name,B,cut,nIter", [("T", 160, 70, 10), ("C4", 200, 77, 5), ("C3", 160, 67, 5)])
+def test_shard_concat_equals_unsharded(name, B, cut, nIter):
     """Samples are independent: solving two row blocks separately equals solving the batch at
     once (what the multi-GPU sharding relies on) -- up to float32 summation order in K1, whose
-    split-K factor follows the grid size."""
+    split-K factor follows the grid size.  Both shards keep >= 64 rows (same K1 path), and the horizons are
+    the ones where the float32 noise floor of the workload is below 1 % (profiles/r02_parity.json), so that a
+    disagreement would be a sharding bug and not a ReLU-kink flip."""
     import icnn_b200
     from icnn_b200 import bundle_entropy as be
-    p, x, y0 = synth.make_inputs("C3", B=80)
+    cfg = synth.CONFIGS[name]
+    p, x, y0 = synth.make_inputs(name, B=B)
     net = icnn_b200.PICNN.from_params(p)
-    full = be.solveBatch(net.bind(x), y0.copy(), nIter=10)
-    a = be.solveBatch(net.bind(x[:37]), y0[:37].copy(), nIter=10)
-    b = be.solveBatch(net.bind(x[37:]), y0[37:].copy(), nIter=10)
+    kw = dict(nIter=nIter, variant=cfg["variant"])
+    full = be.solveBatch(net.bind(x, affine=cfg["affine"]), y0.copy(), **kw)
+    a = be.solveBatch(net.bind(x[:cut], affine=cfg["affine"]), y0[:cut].copy(), **kw)
+    b = be.solveBatch(net.bind(x[cut:], affine=cfg["affine"]), y0[cut:].copy(), **kw)
     d = rowdiff(full[0], np.concatenate([a[0], b[0]]))
-    assert np.median(d) < 1e-5 and np.mean(d < 1e-4) >= 0.9
-    assert np.mean(np.array(full[5]) == np.array(a[5] + b[5])) >= 0.9
+    assert np.median(d) < 1e-5 and np.mean(d < 1e-4) >= 0.97, (np.median(d), np.mean(d < 1e-4))
+    assert np.mean(np.array(full[5]) == np.array(a[5] + b[5])) >= 0.95
 
 
 def test_fused_properties_at_full_size():
@@ -308,7 +315,7 @@ def test_full_size_subsample_matches_oracle(name, nsub):
     """BASELINE.json's configs at FULL size and FULL horizon (C5: 8192 x 4096, 50 iterations, 51 slots): the
     samples are independent (lib/bundle_entropy.py:211), so a random subsample of the device result is compared
     with the float64 oracle run on exactly those rows, next to the oracle's own float32 noise floor on the same
-    rows.  Tolerance: fraction of rows off by more than 1e-4 <= floor + 0.02 (+ one row), median <=
+    rows.  Tolerance: fraction of rows off by more than 1e-4 <= floor + max(0.02, 2.5 rows), median <=
     max(1e-5, 4 x floor median); at the short horizons (C3 / C4 / T) the floor is ~0 and this is the 1e-4 statement."""
     import icnn_b200
     from icnn_b200 import bundle_entropy as be
@@ -334,7 +341,7 @@ def test_full_size_subsample_matches_oracle(name, nsub):
     _parity_record("fullsize_%s" % name, d, floor, {"B": B, "nIter": nIter, "KS": (nIter if variant == "rl" else min(nIter, cfg["n"])) + 1,
                                                    "active_rows_device_mean": float(kdev.mean()),
                                                    "active_rows_oracle_mean": float(lens(o[1]).mean())})
-    assert np.mean(d > 1e-4) <= np.mean(floor > 1e-4) + 0.02 + 1.0 / nsub, (np.mean(d > 1e-4), np.mean(floor > 1e-4))
+    assert np.mean(d > 1e-4) <= np.mean(floor > 1e-4) + max(0.02, 2.5 / nsub), (np.mean(d > 1e-4), np.mean(floor > 1e-4))
     assert np.median(d) <= max(1e-5, 4 * np.median(floor)), (np.median(d), np.median(floor))
     # objective: f - H at the device solution is as good as the oracle's on those rows
     fg64 = picnn_np.make_fg(p, xs, affine=cfg["affine"])

@@ -193,3 +193,24 @@ def test_make_cvx_and_proj():
     np.testing.assert_array_equal(proj([None, w[1].clone()])[1].numpy(), [[0, 2], [0.5, 0]])
     np.testing.assert_array_equal(make_cvx([None, w[1].clone()])[1].numpy(), [[1, 2], [0.5, 4]])
     np.testing.assert_array_equal(make_cvx([None, w[1].clone()], halve=True)[1].numpy(), [[0.5, 1], [0.25, 2]])
+
+
+def test_in_place_weight_updates_must_be_repacked():
+    """The device library keeps packed / TF32-split copies of the weights: after an in-place update of the torch
+    tensors (optimiser step, make_cvx / proj) bind() refuses to run on the stale copies, and
+    update_weights() makes K1, the gate GEMMs and the torch-side x-path agree again."""
+    import icnn_b200
+    from icnn_b200.gd_grad import proj
+    p, x, y0, tY = _dims_case(40, 64, [96, 80], 128, seed=9)
+    net = icnn_b200.PICNN.from_params(p)
+    y = np.random.RandomState(1).uniform(0.1, 0.9, size=y0.shape)
+    f0, _ = net.bind(x)(y)
+    net.Wz[1].mul_(-1.0)            # in-place change ...
+    proj(net.Wz)                    # ... and projection: Wz[1] is now all zeros
+    with pytest.raises(RuntimeError, match="update_weights"):
+        net.bind(x)
+    net.update_weights()
+    f1, _ = net.bind(x)(y)
+    p.Wz[1] = np.zeros_like(p.Wz[1])
+    fo, _ = picnn_np.make_fg(p, x)(y)
+    assert np.abs(f1 - fo).max() <= 1e-5 * max(1.0, np.abs(fo).max()) and np.abs(f1 - f0).max() > 1e-3
