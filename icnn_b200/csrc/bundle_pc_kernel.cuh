@@ -743,7 +743,9 @@ __global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WP
     for (int ch = 0; ch < NCH; ++ch) {
       const int cb = ch * 4 * T;
       if (cb >= n) break;
-#pragma unroll
+      // one warp per sample: keep the log / division body rolled (ncu, C3: 36 % of the warp cycles were
+      // instruction-fetch stalls with the 4x unrolled body; many small CTAs at different code positions per SM)
+#pragma unroll (WPS == 1 ? 1 : 4)
       for (int c = 0; c < 4; ++c) {
         const int e = pc_col<T, VEC>(cb, g.tid, c);
         if (e < n) {
