@@ -471,10 +471,16 @@ def measure_workload(ctx, name, steps, warmup, scaling, solver, cpu_seconds, hea
     k2_flops = k2_fp64_flops(n, stats)
     k2_bytes = 4.0 * n * (ksum + 2.0 * B * its) + 8.0 * ksum
     tr = ctx.traffic.get(name, {})
+
+    def _traffic(kname):
+        t_ = tr.get(kname)
+        if not t_:
+            return None, None
+        return t_["bytes"] * (float(B) / t_["rows"]), "%s; %d rows captured, scaled to %d rows (independent samples)" % (t_["source"], t_["rows"], B)
     roof_k2 = dict(kernel=k2_name, bound="tensor", pipe="fp64 tensor core (DMMA m8n8k4) + FP64 FMA",
                    achieved=k2_flops / (k2_ms * 1e-3) / 1e12, peak=ctx.fp64_peak, unit="TFLOP/s",
                    peak_source="measured live (icnn_fp64_mma_probe, DMMA)",
-                   traffic=tr.get("K2", {}).get("bytes"), traffic_source=tr.get("K2", {}).get("source"),
+                   traffic=_traffic("K2")[0], traffic_source=_traffic("K2")[1],
                    launches=its, ms_per_launch=k2_ms / max(its, 1), share_of_step=k2_ms / (k1_ms + k2_ms),
                    algorithmic_gflop_per_step=k2_flops / 1e9,
                    inner_iterations_per_solve=float(stats[:, 2].sum() / max(stats[:, 0].sum() - stats[:, 5].sum(), 1)),
@@ -490,7 +496,7 @@ def measure_workload(ctx, name, steps, warmup, scaling, solver, cpu_seconds, hea
     nl_k1 = its * (2 * L + 2)
     roof_k1 = dict(kernel=k1_name, bound="tensor", achieved=k1_flops / (k1_ms * 1e-3) / 1e12,
                    peak=peaks["bf16_sustained"], unit="TFLOP/s", peak_source=peaks["source"] + ", bf16 sustained",
-                   traffic=tr.get("K1", {}).get("bytes"), traffic_source=tr.get("K1", {}).get("source"),
+                   traffic=_traffic("K1")[0], traffic_source=_traffic("K1")[1],
                    launches=nl_k1, ms_per_launch=k1_ms / max(nl_k1, 1), share_of_step=k1_ms / (k1_ms + k2_ms),
                    note="FP32-accurate GEMMs as 3 TF32 MMAs per product: the ceiling of this formulation is "
                         "tf32 peak / 3 = bf16 peak / 6",

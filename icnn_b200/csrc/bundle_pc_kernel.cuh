@@ -128,7 +128,7 @@ struct PcRed {
   template <class G>
   __device__ __forceinline__ double sum(const G& g, double v) {
     v = Grp<WPS>::wsum(v);
-    if (WPS == 1) return v;
+    if (WPS == 1) { __syncwarp(); return v; }   // the reduction doubles as the barrier that publishes the n-vectors
     double* r = red + par * 4 * WPS;
     par ^= 1;
     if (g.lane == 0) r[g.warp] = v;
@@ -142,7 +142,7 @@ struct PcRed {
   __device__ __forceinline__ void min2(const G& g, double& a, double& b) {
     a = Grp<WPS>::wmin(a);
     b = Grp<WPS>::wmin(b);
-    if (WPS == 1) return;
+    if (WPS == 1) { __syncwarp(); return; }
     double* r = red + par * 4 * WPS;
     par ^= 1;
     if (g.lane == 0) { r[g.warp] = a; r[WPS + g.warp] = b; }

@@ -138,6 +138,7 @@ __device__ __forceinline__ float tf32_lo(float x, float hi) { return tf32_rn(x -
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;  // fp32 elements per stage row = one 128-byte swizzle span
 constexpr int TC_CH = 1;   // k-blocks per accumulation chunk (K = 32: four accumulations per TMEM accumulator before the RN drain)
+constexpr int TC_SETS = 3; // hi*hi accumulators in flight (+ one cross-term accumulator = 4 x BN TMEM columns)
 
 struct TcArgs {
   int M, N, K;
@@ -187,9 +188,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
   uint64_t* empty = full + SM::NST;
-  uint64_t* acc_full = empty + SM::NST;     // [2] accumulator set s holds a finished chunk
-  uint64_t* acc_empty = acc_full + 2;       // [2] set s has been drained by the four epilogue warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_full = empty + SM::NST;           // [TC_SETS] hi*hi accumulator s holds a finished chunk
+  uint64_t* acc_empty = acc_full + TC_SETS;       // [TC_SETS] accumulator s has been drained by the four epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TC_SETS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
@@ -203,17 +204,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
     for (int s = 0; s < SM::NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < TC_SETS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // Chunked accumulation (round 2).  The tensor core truncates its FP32 accumulator toward zero at every MMA:
   // a systematic relative bias of ~3e-8 per accumulation (tools/tc_bias_probe.py: -1.2e-5 at K = 5120 in one
   // accumulator chain, -1.2e-6 with K cut into 640-slices, -1.7e-7 with 128-slices), which compounds through
   // the layers (C5: f scaled by 1 - 1.1e-5) and moves y* by 3e-3 over 50 bundle iterations.  The reduction is
-  // therefore cut into CHUNKS of TC_CH k-blocks: the MMA warp accumulates one chunk in TMEM accumulator set
-  // (c & 1) -- hi*hi products in one accumulator, the 2^-11 smaller cross terms in a second -- while the four
-  // epilogue warps drain the other set into FP32 REGISTERS with round-to-nearest adds.  4 x BN TMEM columns as
-  // before (2 sets x 2 accumulators).
+  // therefore cut into CHUNKS of TC_CH k-blocks: the MMA warp accumulates the hi*hi products of one chunk in TMEM
+  // accumulator (c % 3) while the four epilogue warps drain the finished ones into FP32 REGISTERS with
+  // round-to-nearest adds.  The 2^-11 smaller cross terms keep ONE accumulator for the whole reduction (their
+  // truncation bias is 2^-11 of 4e-5: nothing) and are added once at the end: the drain reads half the TMEM
+  // bytes and three hi*hi accumulators decouple the MMA issue from the drain.  4 x BN TMEM columns as before.
   if (warp == 1) tmem_alloc(tmem_slot, 4 * BN);
   tc_fence_before();
   __syncthreads();
@@ -240,11 +242,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
       const int nch = (nkb + TC_CH - 1) / TC_CH;
+      const uint32_t xx = tmem_base + (uint32_t)(TC_SETS * BN);
       for (int c = 0; c < nch; ++c) {
-        const int set = c & 1;
-        if (c >= 2) { mbar_wait(&acc_empty[set], (uint32_t)(((c >> 1) - 1) & 1)); tc_fence_after(); }
-        const uint32_t hh = tmem_base + (uint32_t)((2 * set) * BN);
-        const uint32_t xx = tmem_base + (uint32_t)((2 * set + 1) * BN);
+        const int set = c % TC_SETS;
+        if (c >= TC_SETS) { mbar_wait(&acc_empty[set], (uint32_t)(((c / TC_SETS) - 1) & 1)); tc_fence_after(); }
+        const uint32_t hh = tmem_base + (uint32_t)(set * BN);
         const int kb1 = ::min(nkb, (c + 1) * TC_CH);
         for (int kb = c * TC_CH; kb < kb1; ++kb) {
           const int s = kb % SM::NST;
@@ -261,7 +263,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             const uint64_t adv = (uint64_t)((k4 * 8 * 4) >> 4);  // +32 B per k-step inside the swizzle span
             const uint32_t first = (kb == c * TC_CH && k4 == 0) ? 0u : 1u;
             umma_tf32(hh, dAh + adv, dBh + adv, idesc, first);
-            umma_tf32(xx, dAh + adv, dBl + adv, idesc, first);
+            umma_tf32(xx, dAh + adv, dBl + adv, idesc, (kb == 0 && k4 == 0) ? 0u : 1u);
             umma_tf32(xx, dAl + adv, dBh + adv, idesc, 1u);
           }
           umma_commit(&empty[s]);  // stage free once these MMAs have read it
@@ -283,21 +285,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     {
       const int nch = (nkb + TC_CH - 1) / TC_CH;
       for (int c = 0; c < nch; ++c) {
-        const int set = c & 1;
-        mbar_wait(&acc_full[set], (uint32_t)((c >> 1) & 1));
+        const int set = c % TC_SETS;
+        mbar_wait(&acc_full[set], (uint32_t)((c / TC_SETS) & 1));
         tc_fence_after();
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32], w[32];
-          const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((2 * set) * BN + c0);
-          tmem_ld32(tb, v);          // hi*hi
-          tmem_ld32(tb + BN, w);     // cross terms
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * BN + c0), v);   // hi*hi of this chunk
 #pragma unroll
-          for (int j = 0; j < 32; ++j) run[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(w[j]);
+          for (int j = 0; j < 32; ++j) run[c0 + j] += __uint_as_float(v[j]);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[set]);
+      }
+      if (nch > 0) {   // the last acc_full commit covers every MMA issued before it: the cross-term accumulator is final
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t w[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(TC_SETS * BN + c0), w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) run[c0 + j] += __uint_as_float(w[j]);
+        }
       }
     }
     float* tile = reinterpret_cast<float*>(smem) + q * (32 * 33);

@@ -18,7 +18,7 @@ def run(name, B, nIter, variant=None, **kw):
     print(name, B, nIter, variant or cfg["variant"], "ok, y range", float(out[0].min()), float(out[0].max()), flush=True)
     return net, fg, out
 
-which = sys.argv[1:] or ["c1", "c3", "c3dual", "c4", "c2", "t", "k3", "adam", "odd", "gdgrad"]
+which = sys.argv[1:] or ["c1", "c3", "c3dual", "c4", "c2", "t", "k3", "adam", "odd", "gdgrad", "pc"]
 if "c1" in which: run("C1", 16, 4)
 if "c3" in which: run("C3", 6, 4)
 if "c3dual" in which: run("C3", 6, 4, variant="dual")
@@ -48,4 +48,16 @@ if "gdgrad" in which:
         yN, gr = icnn_b200.gd_grad.gd_grad(icnn_b200.PICNN.from_params(p).bind(x), np.full((B, dims[1]), 0.5), tY,
                                            nIter=3, lr=0.02, momentum=0.5, x=x)
         print("gdgrad ok", dims, B, float(np.abs(gr["Wy"][0]).max()), flush=True)
+if "pc" in which:     # round 2: the two-sweep PC kernel in every group size, both alignments, the > 4 row-block sweeps, and
+    # the chunked-accumulation tcgen05 GEMM (T, 64 rows above)
+    run("C3", 5, 5)                                     # 1 warp / sample, n_y % 4 != 0 (scalar row loads)
+    for w in ("1", "2", "4", "8"):
+        os.environ["ICNN_PC_WPS"] = w
+        run("T", 3, 4)                                  # n_y = 512 on 1 / 2 / 4 / 8 warps per sample
+    os.environ["ICNN_PC_WPS"] = "2"
+    run("T", 2, 36)                                     # k + 2 > 32 sweep rows: second triangle + rectangle sweeps
+    os.environ.pop("ICNN_PC_WPS")
+    run("C5", 2, 6)                                     # 16 warps / sample (n_y = 4096)
+    _, _, o = run("C3", 4, 4, stats=True)
+    print("stats", o[-1].stats()["entering"], flush=True)
 print("done")
