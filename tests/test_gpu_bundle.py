@@ -307,15 +307,15 @@ def test_fused_properties_at_full_size_other_configs(name):
         assert np.all(Gu.dot(y[u]) + np.array(h[u]) <= f_star[u] + 1e-3 * max(1, abs(f_star[u])))
 
 
-FULLSIZE = [("C3", 64), ("T", 64), ("C4", 64), ("C2", 48), ("C5", 12)]
+FULLSIZE = [("C3", 64), ("T", 64), ("C4", 64), ("C2", 48), ("C5", 16)]
 
 
 @pytest.mark.parametrize("name,nsub", FULLSIZE)
 def test_full_size_subsample_matches_oracle(name, nsub):
     """BASELINE.json's configs at FULL size and FULL horizon (C5: 8192 x 4096, 50 iterations, 51 slots): the
     samples are independent (lib/bundle_entropy.py:211), so a random subsample of the device result is compared
-    with the float64 oracle run on exactly those rows, next to the oracle's own float32 noise floor on the same
-    rows.  Tolerance: fraction of rows off by more than 1e-4 <= floor + max(0.02, 2.5 rows), median <=
+    with the float64 oracle run on exactly those rows, next to the oracle's own noise floor on the same rows (the
+    larger of: float32-arithmetic fg; float64 fg with 2e-6 relative noise = the device's measured f/g accuracy).  Tolerance: fraction of rows off by more than 1e-4 <= floor + max(0.02, 2.5 rows), median <=
     max(1e-5, 4 x floor median); at the short horizons (C3 / C4 / T) the floor is ~0 and this is the 1e-4 statement."""
     import icnn_b200
     from icnn_b200 import bundle_entropy as be
@@ -331,14 +331,30 @@ def test_full_size_subsample_matches_oracle(name, nsub):
         o = bundle_np.solve_batch(picnn_np.make_fg(p, xs, affine=cfg["affine"]), ys.copy(), nIter=nIter, variant=variant)
         o32 = bundle_np.solve_batch(picnn_np.make_fg(p, xs, affine=cfg["affine"], dtype=np.float32, out_dtype=np.float64),
                                     ys.copy(), nIter=nIter, variant=variant)
+        # second floor: the float64 oracle under a relative perturbation of (f, g) of the size of the device's
+        # measured f/g error (<= 2e-6: tests/test_gpu_picnn.py::test_long_reductions_carry_no_systematic_bias) --
+        # SURVEY.md section 8c asks for both floors; with 12-64 rows one realisation alone is a noisy estimate
+        rsn = np.random.RandomState(123)
+        fg64n = picnn_np.make_fg(p, xs, affine=cfg["affine"])
+
+        def fg_noisy(y):
+            f, g = fg64n(y)
+            return f * (1.0 + 2e-6 * rsn.randn(*f.shape)), g * (1.0 + 2e-6 * rsn.randn(*g.shape))
+        on = bundle_np.solve_batch(fg_noisy, ys.copy(), nIter=nIter, variant=variant)
     d = rowdiff(r[0][rows], o[0])
-    floor = rowdiff(o32[0], o[0])
+    floor32 = rowdiff(o32[0], o[0])
+    floorn = rowdiff(on[0], o[0])
+    floor = floorn if np.mean(floorn > 1e-4) > np.mean(floor32 > 1e-4) else floor32     # the larger of the two floors
     kdev = lens([r[1][int(u)] for u in rows])
     print("\n%s full size, %d-row subsample: device-vs-oracle max %.2e median %.2e frac>1e-4 %.3f | oracle f32 floor max "
           "%.2e median %.2e frac>1e-4 %.3f | active rows device mean %.1f oracle mean %.1f"
           % (name, nsub, d.max(), np.median(d), np.mean(d > 1e-4), floor.max(), np.median(floor), np.mean(floor > 1e-4),
              kdev.mean(), lens(o[1]).mean()))
     _parity_record("fullsize_%s" % name, d, floor, {"B": B, "nIter": nIter, "KS": (nIter if variant == "rl" else min(nIter, cfg["n"])) + 1,
+                                                   "floor_f32_arithmetic_frac_gt_1e-4": float(np.mean(floor32 > 1e-4)),
+                                                   "floor_2e-6_noise_frac_gt_1e-4": float(np.mean(floorn > 1e-4)),
+                                                   "floor_f32_arithmetic_median": float(np.median(floor32)),
+                                                   "floor_2e-6_noise_median": float(np.median(floorn)),
                                                    "active_rows_device_mean": float(kdev.mean()),
                                                    "active_rows_oracle_mean": float(lens(o[1]).mean())})
     assert np.mean(d > 1e-4) <= np.mean(floor > 1e-4) + max(0.02, 2.5 / nsub), (np.mean(d > 1e-4), np.mean(floor > 1e-4))
