@@ -10,6 +10,8 @@ namespace icnn {
 ICNN_PC_DECL(1, 1); ICNN_PC_DECL(1, 2); ICNN_PC_DECL(1, 4); ICNN_PC_DECL(2, 1); ICNN_PC_DECL(2, 2);
 ICNN_PC_DECL(4, 1); ICNN_PC_DECL(4, 2); ICNN_PC_DECL(8, 1); ICNN_PC_DECL(8, 2);
 ICNN_PC_DECL(16, 1); ICNN_PC_DECL(16, 2); ICNN_PC_DECL(16, 4);
+// n-vectors in the caller's scratch instead of shared memory (bundle_pc_e.cu): W = 200 + warps
+ICNN_PC_DECL(201, 4); ICNN_PC_DECL(202, 2); ICNN_PC_DECL(204, 2); ICNN_PC_DECL(208, 4); ICNN_PC_DECL(208, 2);
 // n_y % 4 != 0 (rows not 16-byte aligned): scalar row loads, small groups only (bundle_pc_d.cu)
 ICNN_PC_DECL(101, 1); ICNN_PC_DECL(101, 2); ICNN_PC_DECL(102, 1); ICNN_PC_DECL(102, 2);
 
@@ -19,14 +21,14 @@ ICNN_PC_DECL(1, 4) { return launch_pc<1, 4, true>(a, c, B, st); }
 ICNN_PC_DECL(2, 1) { return launch_pc<2, 1, true>(a, c, B, st); }
 ICNN_PC_DECL(2, 2) { return launch_pc<2, 2, true>(a, c, B, st); }
 
-static bool pc_fits(const icnn_bundle_bufs* b, int wps, int nch, PcConfig* out) {
+static bool pc_fits(const icnn_bundle_bufs* b, int wps, int nch, PcConfig* out, bool gv = false) {
   if (b->n > 128 * wps * nch) return false;
   PcConfig c;
-  c.wps = wps; c.nch = nch;
+  c.wps = wps; c.nch = nch; c.gv = gv;
   c.npad = (b->n + 15) & ~15;   // the tensor-core sweep reads whole 16-column groups of the n-vectors
   c.vec = (b->n & 3) == 0;
   if (!c.vec && wps > 2) return false;
-  c.smem = sizeof(double) * pc_group_doubles(c.npad, b->KS, wps);
+  c.smem = sizeof(double) * pc_group_doubles(c.npad, b->KS, wps, gv);
   if (c.smem > 227 * 1024) return false;
   // 80-register build (768 threads / SM) when shared memory lets that many samples be resident, else 128 registers
   c.minb = (wps == 16) ? 1 : ((c.smem + 1024) * (24 / wps) <= 228 * 1024 ? 3 : 2);
@@ -55,6 +57,17 @@ static bool pick_pc(const icnn_bundle_bufs* b, PcConfig* out) {
   else if (n <= 2048) { wps = 8; nch = 2; }
   else if (n <= 4096) { wps = 16; nch = 2; }
   else { wps = 16; nch = 4; }
+  // ICNN_PC_GV=<warps>: n-vectors in global scratch (exploration / measured dispatch below)
+  if (const char* v = getenv("ICNN_PC_GV")) {
+    const int w = atoi(v);
+    if (b->vec_ws && (n & 3) == 0) {
+      if (w == 1 && n <= 512) return pc_fits(b, 1, 4, out, true);
+      if (w == 2 && n <= 512) return pc_fits(b, 2, 2, out, true);
+      if (w == 4 && n <= 1024) return pc_fits(b, 4, 2, out, true);
+      if (w == 8 && n <= 2048) return pc_fits(b, 8, 2, out, true);
+      if (w == 8 && n <= 4096) return pc_fits(b, 8, 4, out, true);
+    }
+  }
   if (n > 256 && n <= 2048 && !getenv("ICNN_PC_WPS")) return false;
   if (const char* v = getenv("ICNN_PC_WPS")) {
     const int w = atoi(v);
@@ -74,8 +87,13 @@ int bundle_pc_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int 
   PcArgs a;
   a.b = *b; a.c = *cfg; a.t = t; a.npad = c.npad;
   cudaError_t e;
-  const int key = (c.vec ? 0 : 1000) + c.wps * 10 + c.nch;
+  const int key = (c.gv ? 2000 : 0) + (c.vec ? 0 : 1000) + c.wps * 10 + c.nch;
   switch (key) {
+    case 2014: e = launch_pc_201_4(a, c, b->B, st); break;
+    case 2022: e = launch_pc_202_2(a, c, b->B, st); break;
+    case 2042: e = launch_pc_204_2(a, c, b->B, st); break;
+    case 2082: e = launch_pc_208_2(a, c, b->B, st); break;
+    case 2084: e = launch_pc_208_4(a, c, b->B, st); break;
     case 1011: e = launch_pc_101_1(a, c, b->B, st); break;
     case 1012: e = launch_pc_101_2(a, c, b->B, st); break;
     case 1021: e = launch_pc_102_1(a, c, b->B, st); break;

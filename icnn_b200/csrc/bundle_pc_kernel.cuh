@@ -33,8 +33,8 @@ struct PcArgs {
 
 constexpr int PC_NKV = 18;
 
-__host__ __device__ inline size_t pc_group_doubles(int npad, int KS, int wps) {
-  size_t d = (size_t)4 * npad + (size_t)KS * (KS + 1) / 2 + (size_t)PC_NKV * KS + KS /* row pointers */ +
+__host__ __device__ inline size_t pc_group_doubles(int npad, int KS, int wps, bool gv = false) {
+  size_t d = (gv ? (size_t)0 : (size_t)4 * npad) + (size_t)KS * (KS + 1) / 2 + (size_t)PC_NKV * KS + KS /* row pointers */ +
              8 * wps /* two reduction buffers */ + 16 /* scalars */ + 4 /* 8 ints */;
   return (d + 1) & ~(size_t)1;
 }
@@ -167,7 +167,7 @@ __device__ __forceinline__ double dweight(double y) { return fma(-y, y, y); }
 // values, so only the loads of G are predicated.  The warp partials are summed by a fixed tree through a
 // scratch n-vector (deterministic), and warp 0 stores the result (packed matrix / q / w).
 // VEC: rows are 16-byte aligned (n % 4 == 0) -> one 128-bit load per row block.
-template <int WPS, int NA, int NB, bool TRI, bool PSEUDO, bool VEC, class G>
+template <int WPS, int NA, int NB, bool TRI, bool PSEUDO, bool VEC, bool GVL, class G>
 __device__ __forceinline__ void gram_sweep_pc(const G& g, const float* const* rowp, int k, int n, const double* yv,
                                               const double* rv, double* Lp, double* qk, double* wk, double* scratch,
                                               int scap, int a0, int b0) {
@@ -197,12 +197,22 @@ __device__ __forceinline__ void gram_sweep_pc(const G& g, const float* const* ro
 #pragma unroll 1
   for (int gi = g.warp; gi < ngrp; gi += NG * WPS) {
     float4 v[NG][NL];
+    double2 yl[GVL ? NG : 1][2], rl[GVL ? NG : 1][2];   // GVL: y / ry come from L2 as well -> issued with the row loads
 #pragma unroll
     for (int u = 0; u < NG; ++u) {
       const int gu = gi + u * WPS;
       const int off = gu * 16;
       const int col = off + 4 * q;
       const bool gv = (u == 0) || gu < ngrp;
+      if (GVL) {
+        const int og = gv ? off : 0;
+        yl[GVL ? u : 0][0] = *reinterpret_cast<const double2*>(yq + og);
+        yl[GVL ? u : 0][1] = *reinterpret_cast<const double2*>(yq + og + 2);
+        if (PSEUDO && ps && r == 0) {
+          rl[GVL ? u : 0][0] = *reinterpret_cast<const double2*>(rq + og);
+          rl[GVL ? u : 0][1] = *reinterpret_cast<const double2*>(rq + og + 2);
+        }
+      }
 #pragma unroll
       for (int b = 0; b < NL; ++b) {
         v[u][b] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -222,12 +232,14 @@ __device__ __forceinline__ void gram_sweep_pc(const G& g, const float* const* ro
       const int gu = gi + u * WPS;
       if (u > 0 && gu >= ngrp) break;
       const int off = gu * 16;
-      const double2 ya = *reinterpret_cast<const double2*>(yq + off), yb = *reinterpret_cast<const double2*>(yq + off + 2);
+      const double2 ya = GVL ? yl[GVL ? u : 0][0] : *reinterpret_cast<const double2*>(yq + off);
+      const double2 yb = GVL ? yl[GVL ? u : 0][1] : *reinterpret_cast<const double2*>(yq + off + 2);
       double dd[4] = {dweight(ya.x), dweight(ya.y), dweight(yb.x), dweight(yb.y)};
       double pa[4] = {0.0, 0.0, 0.0, 0.0};
       if (PSEUDO && ps) {
         if (r == 0) {
-          const double2 ra = *reinterpret_cast<const double2*>(rq + off), rb = *reinterpret_cast<const double2*>(rq + off + 2);
+          const double2 ra = GVL ? rl[GVL ? u : 0][0] : *reinterpret_cast<const double2*>(rq + off);
+          const double2 rb = GVL ? rl[GVL ? u : 0][1] : *reinterpret_cast<const double2*>(rq + off + 2);
           pa[0] = dd[0] * ra.x; pa[1] = dd[1] * ra.y; pa[2] = dd[2] * rb.x; pa[3] = dd[3] * rb.y;
         } else {
           pa[0] = ya.x; pa[1] = ya.y; pa[2] = yb.x; pa[3] = yb.y;
@@ -322,29 +334,29 @@ __device__ __forceinline__ void gram_sweep_pc(const G& g, const float* const* ro
   }
 }
 
-template <int WPS, int NB, bool VEC, class G>
+template <int WPS, int NB, bool VEC, bool GVL, class G>
 __device__ __forceinline__ void gram_rect_pair_pc(const G& g, const float* const* rowp, int k, int n, const double* yv,
                                                   const double* rv, double* Lp, double* qk, double* wk, double* sx, int scap) {
-  gram_sweep_pc<WPS, 2, NB, false, true, VEC>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 0, 4);
-  gram_sweep_pc<WPS, 2, NB, false, false, VEC>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 2, 4);
+  gram_sweep_pc<WPS, 2, NB, false, true, VEC, GVL>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 0, 4);
+  gram_sweep_pc<WPS, 2, NB, false, false, VEC, GVL>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 2, 4);
 }
 
 // k + 2 sweep rows in rb = ceil((k + 2) / 8) <= 8 row blocks (k <= 62).  On return warp 0 has stored M0, q, w.
-template <int WPS, bool VEC, class G>
+template <int WPS, bool VEC, bool GVL, class G>
 __device__ __forceinline__ void gram_pass_pc(const G& g, const float* const* rowp, int k, int n, const double* yv,
                                              const double* rv, double* Lp, double* qk, double* wk, double* sx, int scap) {
   const int rb = (k + 2 + 7) >> 3;
-  if (rb == 1) gram_sweep_pc<WPS, 1, 1, true, true, VEC>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 0, 0);
-  else if (rb == 2) gram_sweep_pc<WPS, 2, 2, true, true, VEC>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 0, 0);
-  else if (rb == 3) gram_sweep_pc<WPS, 3, 3, true, true, VEC>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 0, 0);
+  if (rb == 1) gram_sweep_pc<WPS, 1, 1, true, true, VEC, GVL>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 0, 0);
+  else if (rb == 2) gram_sweep_pc<WPS, 2, 2, true, true, VEC, GVL>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 0, 0);
+  else if (rb == 3) gram_sweep_pc<WPS, 3, 3, true, true, VEC, GVL>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 0, 0);
   else {
-    gram_sweep_pc<WPS, 4, 4, true, true, VEC>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 0, 0);
+    gram_sweep_pc<WPS, 4, 4, true, true, VEC, GVL>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 0, 0);
     if (rb > 4) {
       const int r2 = rb - 4;
-      if (r2 == 1) { gram_sweep_pc<WPS, 1, 1, true, false, VEC>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 4, 4); gram_rect_pair_pc<WPS, 1, VEC>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap); }
-      else if (r2 == 2) { gram_sweep_pc<WPS, 2, 2, true, false, VEC>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 4, 4); gram_rect_pair_pc<WPS, 2, VEC>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap); }
-      else if (r2 == 3) { gram_sweep_pc<WPS, 3, 3, true, false, VEC>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 4, 4); gram_rect_pair_pc<WPS, 3, VEC>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap); }
-      else { gram_sweep_pc<WPS, 4, 4, true, false, VEC>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 4, 4); gram_rect_pair_pc<WPS, 4, VEC>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap); }
+      if (r2 == 1) { gram_sweep_pc<WPS, 1, 1, true, false, VEC, GVL>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 4, 4); gram_rect_pair_pc<WPS, 1, VEC, GVL>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap); }
+      else if (r2 == 2) { gram_sweep_pc<WPS, 2, 2, true, false, VEC, GVL>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 4, 4); gram_rect_pair_pc<WPS, 2, VEC, GVL>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap); }
+      else if (r2 == 3) { gram_sweep_pc<WPS, 3, 3, true, false, VEC, GVL>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 4, 4); gram_rect_pair_pc<WPS, 3, VEC, GVL>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap); }
+      else { gram_sweep_pc<WPS, 4, 4, true, false, VEC, GVL>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap, 4, 4); gram_rect_pair_pc<WPS, 4, VEC, GVL>(g, rowp, k, n, yv, rv, Lp, qk, wk, sx, scap); }
     }
   }
 }
@@ -392,7 +404,10 @@ __device__ __forceinline__ void ratio_min(double& nm, double& dn, double a, doub
 // One CTA of WPS warps per sample (the block scheduler balances the SMs at sample granularity: with several
 // samples per CTA the last, partly filled wave costs a whole extra round);  NCH = chunks of 4 T columns per
 // thread (n <= 4 T NCH);  R80: 80-register build (768 threads / SM) instead of 128 registers (512 / SM).
-template <int WPS, int NCH, bool R80, bool VEC>
+// GV: the four n-vectors of a sample live in the caller's scratch (icnn_bundle_bufs::vec_ws, L2-resident) instead of
+// shared memory: shared memory per sample drops to the k x k part, so the samples in flight per SM are bounded by
+// registers / threads only and the one-warp k x k stage of one sample overlaps the sweeps of the others.
+template <int WPS, int NCH, bool R80, bool VEC, bool GV = false>
 __global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WPS) bundle_pc_kernel(PcArgs A) {
   const icnn_bundle_bufs& b = A.b;
   const icnn_bundle_cfg& cf = A.c;
@@ -411,12 +426,12 @@ __global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WP
   if (b.finished[u]) return;
 
   const int n = b.n, KS = b.KS, npad = A.npad;
-  double* base = smem_d + (size_t)g.gid * pc_group_doubles(npad, KS, WPS);
-  double* yv = base;
+  double* base = smem_d + (size_t)g.gid * pc_group_doubles(npad, KS, WPS, GV);
+  double* yv = GV ? b.vec_ws + (size_t)u * 4 * npad : base;
   double* uv = yv + npad;
   double* rv = uv + npad;   // ry, then du
   double* xv = rv + npad;   // v1 + v3, then dy ; scratch of the dependency test and of the sweep-A tree sum
-  double* Lp = xv + npad;   // packed lower k x k
+  double* Lp = GV ? base : xv + npad;   // packed lower k x k
   double* kv = Lp + (size_t)KS * (KS + 1) / 2;
 #define PCKV(i) (kv + (i) * KS)
   double* hk = PCKV(0);
@@ -604,7 +619,7 @@ __global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WP
     double* zc = PCKV(1 + zsel);
     double* scur = PCKV(3 + zsel);
     // ---- sweep A (warp 0 ends up holding M0, q, w in shared memory)
-    gram_pass_pc<WPS, VEC>(g, rowp, k, n, yv, rv, Lp, qk, wk, xv, npad);
+    gram_pass_pc<WPS, VEC, GV>(g, rowp, k, n, yv, rv, Lp, qk, wk, xv, npad);
     // ---- k x k stage
     if (g.warp == 0) {
       const int lane = g.lane;
@@ -804,13 +819,13 @@ __global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WP
 #undef PCKV
 }
 
-struct PcConfig { int wps, nch, npad, minb; bool vec; size_t smem; };
+struct PcConfig { int wps, nch, npad, minb; bool vec, gv; size_t smem; };
 
-template <int WPS, int NCH, bool VEC>
+template <int WPS, int NCH, bool VEC, bool GV = false>
 static cudaError_t launch_pc(const PcArgs& a, const PcConfig& c, int B, cudaStream_t st) {
   void (*kern)(PcArgs);
-  if constexpr (WPS == 16) kern = bundle_pc_kernel<16, NCH, false, VEC>;
-  else kern = (c.minb >= 3) ? bundle_pc_kernel<WPS, NCH, true, VEC> : bundle_pc_kernel<WPS, NCH, false, VEC>;
+  if constexpr (WPS == 16) kern = bundle_pc_kernel<16, NCH, false, VEC, GV>;
+  else kern = (c.minb >= 3) ? bundle_pc_kernel<WPS, NCH, true, VEC, GV> : bundle_pc_kernel<WPS, NCH, false, VEC, GV>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
   if (e != cudaSuccess) return e;
   kern<<<(unsigned)B, WPS * 32, c.smem, st>>>(a);

@@ -109,6 +109,9 @@ typedef struct {
                         [5] samples stopped in this iteration (rank / convergence / non-finite)
                         [6] sum of f(y_t) - H(y_t) over the samples entering the iteration (0 log 0 = 0)
                         [7] reserved                                                                  */
+  double* vec_ws;    /* optional (may be NULL): device scratch of B * 4 * ((n + 15) & ~15) doubles.  When set, the
+                        predictor-corrector kernel may keep a sample's four n-vectors (y, u, ry, dy) there (L2-resident)
+                        instead of in shared memory, which multiplies the samples in flight per SM    */
 } icnn_bundle_bufs;
 #define ICNN_NSTAT 8
 

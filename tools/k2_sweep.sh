@@ -1,9 +1,6 @@
 #!/bin/bash
-# K2 configuration sweep (exploration): per-config total K1/K2 ms from tools/iter_profile.py
-for spec in "T 1 2" "T 2 2" "C3 1 2" ; do
+for spec in "T 1 2" "T 1 3" "T 2 3" "T 2 2" "T 4 3" "C2 8 3" "C2 8 2" "C2 4 3"; do
   set -- $spec
-  echo "== $1 ICNN_PC_WPS=$2 MINB=$3"; ICNN_PC_MINB=$3 ICNN_PC_WPS=$2 python tools/iter_profile.py $1 2>&1 | grep -E "total|t= 0|t= 9"
+  echo "== $1 ICNN_PC_GV=$2 MINB=$3"; ICNN_PC_MINB=$3 ICNN_PC_GV=$2 python tools/iter_profile.py $1 2>&1 | grep -E "total"
 done
-echo "== default T"; python tools/iter_profile.py T 2>&1 | grep -E "total"
-echo "== default C3"; python tools/iter_profile.py C3 2>&1 | grep -E "total"
-echo "== default C2"; python tools/iter_profile.py C2 2>&1 | grep -E "total"
+echo "== C5/1024 GV=8 MINB=3 (hoisted loads)"; ICNN_PC_MINB=3 ICNN_PC_GV=8 python tools/iter_profile.py C5 pc 1024 2>&1 | grep -E "total"
