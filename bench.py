@@ -396,6 +396,40 @@ def measure_workload(ctx, name, steps, warmup, scaling, solver, cpu_seconds, hea
     ms_per_step = allmax(sum(a.elapsed_time(b) for a, b in ev)) / steps
     value = Bglob * its / (ms_per_step * 1e-3)
 
+    # ---- the same loop replayed from a CUDA graph (icnn_loop_graph_*): device time and HOST enqueue time of both
+    # forms -- what "launch-bound or not" means for this workload
+    loop_graph = None
+    if world == 1 and os.environ.get("ICNN_BENCH_GRAPH", "1") != "0":
+        gh = st.loop_graph(fg, ccfg)
+        gsteps = steps if ms_per_step < 200.0 else min(steps, 3)
+
+        def step_graph():
+            st.y.copy_(y0_dev)
+            _capi.check(_capi.lib.icnn_loop_graph_launch(gh, stream))
+
+        def enqueue_ms(fn, reps=3):
+            tt = 0.0
+            for _ in range(reps):
+                torch.cuda.synchronize()
+                t0_ = time.perf_counter()
+                fn()
+                tt += time.perf_counter() - t0_
+            torch.cuda.synchronize()
+            return tt / reps * 1e3
+        for _ in range(2):
+            step_graph()
+        torch.cuda.synchronize()
+        gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(gsteps)]
+        for s in range(gsteps):
+            flush.fill_(s & 0xFF)
+            gev[s][0].record()
+            step_graph()
+            gev[s][1].record()
+        torch.cuda.synchronize()
+        loop_graph = {"ms_per_step": sum(a.elapsed_time(b) for a, b in gev) / gsteps, "eager_ms_per_step": ms_per_step,
+                      "steps": gsteps, "kernel_nodes": int(_capi.lib.icnn_loop_graph_nodes(gh)),
+                      "host_enqueue_ms": {"eager": enqueue_ms(step_device), "graph": enqueue_ms(step_graph)}}
+
     # ---- end to end through the public API, host buffers -------------------------------------
     def step_e2e():
         if world > 1 and strong:
@@ -465,7 +499,9 @@ def measure_workload(ctx, name, steps, warmup, scaling, solver, cpu_seconds, hea
     tc_on = B >= 64 and not os.environ.get("ICNN_K1", "tc").startswith("s")
     small = n <= 8 and KS <= 10
     k2_name = ("bundle_step_small_kernel (one thread per sample)" if small else
-               "bundle_pc_kernel (two-sweep PC, DMMA)" if (solver == "pc" and variant == "lib" and (n <= 256 or n > 2048))
+               "bundle_pc_kernel<8 warps, three n-vectors> (two-sweep PC, DMMA; two samples per SM)"
+               if (solver == "pc" and variant == "lib" and 2048 < n <= 4096 and n % 4 == 0 and os.environ.get("ICNN_PC_V3", "") != "0")
+               else "bundle_pc_kernel (two-sweep PC, DMMA)" if (solver == "pc" and variant == "lib" and (n <= 256 or n > 2048))
                else "bundle_step_kernel (DMMA Gram, FP64)")
     # K2: bound by the FP64 pipe (DMMA Gram + FP64 vector work); SURVEY.md 8d's HBM model kept beside it
     k2_flops = k2_fp64_flops(n, stats)
@@ -513,6 +549,7 @@ def measure_workload(ctx, name, steps, warmup, scaling, solver, cpu_seconds, hea
         "per_iteration": {"entering": stats[:its, 0].tolist(), "mean_k": (stats[:its, 1] / np.maximum(stats[:its, 0] - stats[:its, 5], 1)).round(2).tolist(),
                           "mean_f_minus_H": (stats[:its, 6] / np.maximum(stats[:its, 0], 1)).round(4).tolist()} if headline else None,
         "wall_s_timed_region": t_wall,
+        "loop_graph": loop_graph,
     }
     if clk:
         rec["clocks"] = clk.summary()

@@ -13,7 +13,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libicnn_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 NSTAT = 8
 
 # status / enum mirrors of include/icnn_b200.h
@@ -30,6 +30,7 @@ SYMBOLS = [
     "icnn_picnn_set_xpath", "icnn_picnn_gates_workspace_bytes", "icnn_picnn_gates",
     "icnn_adam_workspace_bytes", "icnn_adam_solve",
     "icnn_gd_backward_workspace_bytes", "icnn_gd_backward", "icnn_fp64_mma_probe",
+    "icnn_loop_graph_create", "icnn_loop_graph_launch", "icnn_loop_graph_nodes", "icnn_loop_graph_destroy",
 ]
 
 _fpp = C.POINTER(C.c_void_p)
@@ -110,6 +111,12 @@ def _load():
     lib.icnn_gd_backward.argtypes = [C.c_void_p, C.POINTER(Gates), C.c_void_p, C.c_void_p, C.c_float, C.c_int32,
                                      C.c_float, C.c_float, C.c_void_p, C.POINTER(GdGrads), C.c_void_p, C.c_void_p]
     lib.icnn_fp64_mma_probe.argtypes = [C.c_int32, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
+    lib.icnn_loop_graph_create.argtypes = [C.c_void_p, C.POINTER(Gates), C.POINTER(BundleCfg), C.POINTER(BundleBufs),
+                                           C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.icnn_loop_graph_launch.argtypes = [C.c_void_p, C.c_void_p]
+    lib.icnn_loop_graph_nodes.argtypes = [C.c_void_p]
+    lib.icnn_loop_graph_nodes.restype = C.c_int64
+    lib.icnn_loop_graph_destroy.argtypes = [C.c_void_p]
     for name in SYMBOLS:
         getattr(lib, name)  # AttributeError if the .so does not export it
     if lib.icnn_abi_version() != ABI_VERSION:

@@ -12,6 +12,8 @@ ICNN_PC_DECL(4, 1); ICNN_PC_DECL(4, 2); ICNN_PC_DECL(8, 1); ICNN_PC_DECL(8, 2);
 ICNN_PC_DECL(16, 1); ICNN_PC_DECL(16, 2); ICNN_PC_DECL(16, 4);
 // n-vectors in the caller's scratch instead of shared memory (bundle_pc_e.cu): W = 200 + warps
 ICNN_PC_DECL(201, 4); ICNN_PC_DECL(202, 2); ICNN_PC_DECL(204, 2); ICNN_PC_DECL(208, 4); ICNN_PC_DECL(208, 2);
+// three n-vectors per sample (V3, bundle_pc_f.cu): two samples per SM at n_y = 4096: W = 300 + warps
+ICNN_PC_DECL(308, 4); ICNN_PC_DECL(304, 4);
 // n_y % 4 != 0 (rows not 16-byte aligned): scalar row loads, small groups only (bundle_pc_d.cu)
 ICNN_PC_DECL(101, 1); ICNN_PC_DECL(101, 2); ICNN_PC_DECL(102, 1); ICNN_PC_DECL(102, 2);
 
@@ -21,15 +23,21 @@ ICNN_PC_DECL(1, 4) { return launch_pc<1, 4, true>(a, c, B, st); }
 ICNN_PC_DECL(2, 1) { return launch_pc<2, 1, true>(a, c, B, st); }
 ICNN_PC_DECL(2, 2) { return launch_pc<2, 2, true>(a, c, B, st); }
 
-static bool pc_fits(const icnn_bundle_bufs* b, int wps, int nch, PcConfig* out, bool gv = false) {
+static bool pc_fits(const icnn_bundle_bufs* b, int wps, int nch, PcConfig* out, bool gv = false, bool v3 = false) {
   if (b->n > 128 * wps * nch) return false;
   PcConfig c;
-  c.wps = wps; c.nch = nch; c.gv = gv;
+  c.wps = wps; c.nch = nch; c.gv = gv; c.v3 = v3;
   c.npad = (b->n + 15) & ~15;   // the tensor-core sweep reads whole 16-column groups of the n-vectors
   c.vec = (b->n & 3) == 0;
   if (!c.vec && wps > 2) return false;
-  c.smem = sizeof(double) * pc_group_doubles(c.npad, b->KS, wps, gv);
+  c.smem = sizeof(double) * pc_group_doubles(c.npad, b->KS, wps, gv, v3);
   if (c.smem > 227 * 1024) return false;
+  if (v3) {   // only worth it when at least two samples fit an SM (228 KB, 1 KB reserved per CTA)
+    if (!c.vec || 2 * (c.smem + 1024) > 228 * 1024) return false;
+    c.minb = 2;
+    *out = c;
+    return true;
+  }
   // 80-register build (768 threads / SM) when shared memory lets that many samples be resident, else 128 registers
   c.minb = (wps == 16) ? 1 : ((c.smem + 1024) * (24 / wps) <= 228 * 1024 ? 3 : 2);
   if (wps == 1) c.minb = 2;   // one warp per sample: the 128-register build (no spills) wins (C3 4.5 vs 5.2 ms)
@@ -68,6 +76,15 @@ static bool pick_pc(const icnn_bundle_bufs* b, PcConfig* out) {
       if (w == 8 && n <= 4096) return pc_fits(b, 8, 4, out, true);
     }
   }
+  // three-vector build: ICNN_PC_V3=0 disables it, =1 also tries it for 1024 < n_y <= 2048 (exploration)
+  {
+    const char* v3 = getenv("ICNN_PC_V3");
+    const bool off = v3 && v3[0] == '0', force = v3 && v3[0] == '1';
+    if (!off && !getenv("ICNN_PC_WPS") && (n & 3) == 0) {
+      if (n > 2048 && n <= 4096 && pc_fits(b, 8, 4, out, false, true)) return true;
+      if (force && n > 1024 && n <= 2048 && pc_fits(b, 4, 4, out, false, true)) return true;
+    }
+  }
   if (n > 256 && n <= 2048 && !getenv("ICNN_PC_WPS")) return false;
   if (const char* v = getenv("ICNN_PC_WPS")) {
     const int w = atoi(v);
@@ -87,8 +104,10 @@ int bundle_pc_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int 
   PcArgs a;
   a.b = *b; a.c = *cfg; a.t = t; a.npad = c.npad;
   cudaError_t e;
-  const int key = (c.gv ? 2000 : 0) + (c.vec ? 0 : 1000) + c.wps * 10 + c.nch;
+  const int key = (c.v3 ? 3000 : 0) + (c.gv ? 2000 : 0) + (c.vec ? 0 : 1000) + c.wps * 10 + c.nch;
   switch (key) {
+    case 3084: e = launch_pc_308_4(a, c, b->B, st); break;
+    case 3044: e = launch_pc_304_4(a, c, b->B, st); break;
     case 2014: e = launch_pc_201_4(a, c, b->B, st); break;
     case 2022: e = launch_pc_202_2(a, c, b->B, st); break;
     case 2042: e = launch_pc_204_2(a, c, b->B, st); break;
@@ -113,7 +132,7 @@ int bundle_pc_launch(const icnn_bundle_cfg* cfg, const icnn_bundle_bufs* b, int 
     default: return ICNN_E_UNSUPPORTED;
   }
   if (e != cudaSuccess) {
-    set_error("bundle_pc launch (wps=%d nch=%d smem=%zu): %s", c.wps, c.nch, c.smem, cudaGetErrorString(e));
+    set_error("bundle_pc launch (wps=%d nch=%d v3=%d smem=%zu): %s", c.wps, c.nch, (int)c.v3, c.smem, cudaGetErrorString(e));
     return ICNN_E_CUDA;
   }
   return ICNN_OK;

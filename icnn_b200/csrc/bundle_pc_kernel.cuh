@@ -19,6 +19,14 @@
 //
 // Shared memory per sample: 4 n-vectors (y, u, ry|du, v1+v3|dy), ONE packed lower-triangular k x k matrix,
 // 18 k-vectors.  All reductions over n_y and all k x k algebra are FP64, as in the reference.
+//
+// V3 build (three n-vectors: y, ry, v1+v3|du): for n_y where four FP64 n-vectors leave room for ONE sample per SM
+// (n_y = 4096: 128 KB) the kernel is latency-bound on that one sample's serial stages (the one-warp k x k
+// factor/solves, the tree sums); with three vectors and 12 aliased k-vectors a sample needs <= 113 KB, so TWO
+// 8-warp samples are resident per SM and one sample's serial stage overlaps the other's sweeps.  u = G^T z is
+// not stored: u_old = ry_old - logit(y_old) is recovered in the update (one more log per element per
+// interior-point iteration), and dy = -D (ry + du) is recomputed there from the stored du (same expression,
+// same inputs -> the same bits as the value the step bound was taken from).
 #pragma once
 #include "bundle_step_kernel.cuh"
 
@@ -32,9 +40,11 @@ struct PcArgs {
 };
 
 constexpr int PC_NKV = 18;
+constexpr int PC_NKV_V3 = 12;   // V3: tk / ek / rk (append + dependency test, commit) alias dza / dzp / dzq (IPM only)
 
-__host__ __device__ inline size_t pc_group_doubles(int npad, int KS, int wps, bool gv = false) {
-  size_t d = (gv ? (size_t)0 : (size_t)4 * npad) + (size_t)KS * (KS + 1) / 2 + (size_t)PC_NKV * KS + KS /* row pointers */ +
+__host__ __device__ inline size_t pc_group_doubles(int npad, int KS, int wps, bool gv = false, bool v3 = false) {
+  size_t d = (gv ? (size_t)0 : (size_t)(v3 ? 3 : 4) * npad) + (size_t)KS * (KS + 1) / 2 +
+             (size_t)(v3 ? PC_NKV_V3 : PC_NKV) * KS + KS /* row pointers */ +
              8 * wps /* two reduction buffers */ + 16 /* scalars */ + 4 /* 8 ints */;
   return (d + 1) & ~(size_t)1;
 }
@@ -407,8 +417,9 @@ __device__ __forceinline__ void ratio_min(double& nm, double& dn, double a, doub
 // GV: the four n-vectors of a sample live in the caller's scratch (icnn_bundle_bufs::vec_ws, L2-resident) instead of
 // shared memory: shared memory per sample drops to the k x k part, so the samples in flight per SM are bounded by
 // registers / threads only and the one-warp k x k stage of one sample overlaps the sweeps of the others.
-template <int WPS, int NCH, bool R80, bool VEC, bool GV = false>
+template <int WPS, int NCH, bool R80, bool VEC, bool GV = false, bool V3 = false>
 __global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WPS) bundle_pc_kernel(PcArgs A) {
+  static_assert(!(GV && V3), "V3 is a shared-memory layout");
   const icnn_bundle_bufs& b = A.b;
   const icnn_bundle_cfg& cf = A.c;
   if (b.nactive[A.t] == 0) return;
@@ -426,11 +437,11 @@ __global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WP
   if (b.finished[u]) return;
 
   const int n = b.n, KS = b.KS, npad = A.npad;
-  double* base = smem_d + (size_t)g.gid * pc_group_doubles(npad, KS, WPS, GV);
+  double* base = smem_d + (size_t)g.gid * pc_group_doubles(npad, KS, WPS, GV, V3);
   double* yv = GV ? b.vec_ws + (size_t)u * 4 * npad : base;
-  double* uv = yv + npad;
-  double* rv = uv + npad;   // ry, then du
-  double* xv = rv + npad;   // v1 + v3, then dy ; scratch of the dependency test and of the sweep-A tree sum
+  double* uv = V3 ? nullptr : yv + npad;   // V3: u is not stored (recovered as ry - logit(y) in the update)
+  double* rv = V3 ? yv + npad : uv + npad;   // ry, then du (V3: ry only)
+  double* xv = rv + npad;   // v1 + v3, then dy (V3: then du) ; scratch of the dependency test and of the sweep-A tree sum
   double* Lp = GV ? base : xv + npad;   // packed lower k x k
   double* kv = Lp + (size_t)KS * (KS + 1) / 2;
 #define PCKV(i) (kv + (i) * KS)
@@ -442,10 +453,11 @@ __global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WP
   double* dzq = PCKV(9);
   double* dsa = PCKV(10);
   double* invd = PCKV(11);
-  double* tk = PCKV(12);
-  double* ek = PCKV(13);
-  double* rk = PCKV(14);
-  const float** rowp = reinterpret_cast<const float**>(kv + (size_t)PC_NKV * KS);
+  // V3: these three live in the append / dependency test and (tk) the commit only; dza / dzp / dzq in the IPM loop only
+  double* tk = PCKV(V3 ? 7 : 12);
+  double* ek = PCKV(V3 ? 8 : 13);
+  double* rk = PCKV(V3 ? 9 : 14);
+  const float** rowp = reinterpret_cast<const float**>(kv + (size_t)(V3 ? PC_NKV_V3 : PC_NKV) * KS);
   PcRed<WPS> red;
   red.red = reinterpret_cast<double*>(rowp + KS);
   red.par = 0;
@@ -607,7 +619,7 @@ __global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WP
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int e = pc_col<T, VEC>(cb, g.tid, c);
-        if (e < n) { yv[e] = 0.5; uv[e] = acc[0][c]; rv[e] = acc[0][c]; pr = fma(acc[0][c], acc[0][c], pr); }
+        if (e < n) { yv[e] = 0.5; if (!V3) uv[e] = acc[0][c]; rv[e] = acc[0][c]; pr = fma(acc[0][c], acc[0][c], pr); }
       }
     }
   }
@@ -734,8 +746,8 @@ __global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WP
           const double dy = -dweight(ye) * (rv[e] + du);
           if (dy < 0.0) ratio_min(n1, d1, ye, -dy);
           if (dy > 0.0) ratio_min(n2, d2, 1.0 - ye, dy);
-          xv[e] = dy;
-          rv[e] = du;
+          if (V3) xv[e] = du;            // ry stays in rv; dy is recomputed in the update
+          else { xv[e] = dy; rv[e] = du; }
         }
       }
     }
@@ -764,11 +776,22 @@ __global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WP
       for (int c = 0; c < 4; ++c) {
         const int e = pc_col<T, VEC>(cb, g.tid, c);
         if (e < n) {
-          const double ye = fma(a, xv[e], yv[e]);
-          const double ue = fma(a, rv[e], uv[e]);
-          const double r = log(ye / (1.0 - ye)) + ue;
-          yv[e] = ye; uv[e] = ue; rv[e] = r;
-          pr = fma(r, r, pr);
+          if (V3) {
+            const double yo = yv[e], ro = rv[e], du = xv[e];
+            const double dy = -dweight(yo) * (ro + du);            // the expression of the pass above, same inputs
+            const double uo = ro - log(yo / (1.0 - yo));           // u = ry - logit(y)
+            const double ye = fma(a, dy, yo);
+            const double ue = fma(a, du, uo);
+            const double r = log(ye / (1.0 - ye)) + ue;
+            yv[e] = ye; rv[e] = r;
+            pr = fma(r, r, pr);
+          } else {
+            const double ye = fma(a, xv[e], yv[e]);
+            const double ue = fma(a, rv[e], uv[e]);
+            const double r = log(ye / (1.0 - ye)) + ue;
+            yv[e] = ye; uv[e] = ue; rv[e] = r;
+            pr = fma(r, r, pr);
+          }
         }
       }
     }
@@ -819,15 +842,20 @@ __global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WP
 #undef PCKV
 }
 
-struct PcConfig { int wps, nch, npad, minb; bool vec, gv; size_t smem; };
+struct PcConfig { int wps, nch, npad, minb; bool vec, gv, v3; size_t smem; };
 
-template <int WPS, int NCH, bool VEC, bool GV = false>
+template <int WPS, int NCH, bool VEC, bool GV = false, bool V3 = false>
 static cudaError_t launch_pc(const PcArgs& a, const PcConfig& c, int B, cudaStream_t st) {
   void (*kern)(PcArgs);
-  if constexpr (WPS == 16) kern = bundle_pc_kernel<16, NCH, false, VEC, GV>;
+  if constexpr (V3) kern = bundle_pc_kernel<WPS, NCH, false, VEC, false, true>;   // 128-register build, two CTAs per SM
+  else if constexpr (WPS == 16) kern = bundle_pc_kernel<16, NCH, false, VEC, GV>;
   else kern = (c.minb >= 3) ? bundle_pc_kernel<WPS, NCH, true, VEC, GV> : bundle_pc_kernel<WPS, NCH, false, VEC, GV>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
   if (e != cudaSuccess) return e;
+  if constexpr (V3) {   // the whole point is two 113 KB samples per SM: ask for the largest shared-memory carve-out
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+  }
   kern<<<(unsigned)B, WPS * 32, c.smem, st>>>(a);
   return cudaGetLastError();
 }

@@ -82,3 +82,61 @@ extern "C" int icnn_solve_batch_fused(const icnn_picnn_t* h, const icnn_gates* g
   }
   return ICNN_OK;
 }
+
+// ---- device-side loop as a CUDA graph ------------------------------------------------------------
+// The nIter x (K1, K2) sequence is static: iterations after every sample has finished are device-side
+// no-ops (nactive[t] == 0), so the whole solveBatch body can be captured once and replayed with ONE
+// launch per call.  Every device pointer reachable from the arguments is
+// baked into the graph: the caller replays it only while those buffers are alive and unchanged.
+struct icnn_loop_graph {
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+  size_t nodes;
+};
+
+extern "C" int icnn_loop_graph_create(const icnn_picnn_t* h, const icnn_gates* gates, const icnn_bundle_cfg* cfg,
+                                      const icnn_bundle_bufs* b, void* workspace, icnn_loop_graph_t** out) {
+  ICNN_REQUIRE(out, "null out");
+  *out = nullptr;
+  cudaStream_t cs = nullptr;
+  ICNN_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  // relaxed mode: the first launch of a kernel may load its module lazily inside the capture
+  cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed);
+  if (e != cudaSuccess) { cudaStreamDestroy(cs); set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
+  const int rc = icnn_solve_batch_fused(h, gates, cfg, b, workspace, cs);
+  cudaGraph_t g = nullptr;
+  e = cudaStreamEndCapture(cs, &g);
+  cudaStreamDestroy(cs);
+  if (rc) { if (g) cudaGraphDestroy(g); return rc; }   // icnn_last_error() holds the enqueue error
+  if (e != cudaSuccess || !g) { set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e)); return ICNN_E_CUDA; }
+  icnn_loop_graph* lg = new icnn_loop_graph();
+  lg->graph = g;
+  lg->exec = nullptr;
+  lg->nodes = 0;
+  cudaGraphGetNodes(g, nullptr, &lg->nodes);
+  e = cudaGraphInstantiate(&lg->exec, g, 0);
+  if (e != cudaSuccess) {
+    cudaGraphDestroy(g);
+    delete lg;
+    set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    return ICNN_E_CUDA;
+  }
+  *out = lg;
+  return ICNN_OK;
+}
+
+extern "C" int icnn_loop_graph_launch(icnn_loop_graph_t* g, void* stream) {
+  ICNN_REQUIRE(g && g->exec, "null graph");
+  ICNN_CUDA_CHECK(cudaGraphLaunch(g->exec, static_cast<cudaStream_t>(stream)));
+  return ICNN_OK;
+}
+
+extern "C" int64_t icnn_loop_graph_nodes(const icnn_loop_graph_t* g) { return g ? (int64_t)g->nodes : 0; }
+
+extern "C" int icnn_loop_graph_destroy(icnn_loop_graph_t* g) {
+  if (!g) return ICNN_OK;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+  return ICNN_OK;
+}

@@ -86,6 +86,7 @@ class PICNN:
             elif rc != -3:           # -3 = ICNN_E_UNSUPPORTED (width not a multiple of 4 / SIMT-only build)
                 _capi.check(rc)
         self._versions = [t._version for t in self._weight_tensors()]
+        self._pack_gen = getattr(self, "_pack_gen", 0) + 1   # captured loop graphs bake the packed buffers in
 
     def update_weights(self):
         """Re-pack after the weight tensors were modified in place (an optimiser step, makeCvx / proj:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ICNN_ABI_VERSION 2
+#define ICNN_ABI_VERSION 3
 
 #define ICNN_OK 0
 #define ICNN_E_INVALID (-1)  /* bad argument */
@@ -190,6 +190,19 @@ int icnn_argmin_grad(const icnn_bundle_bufs* b, int32_t loss, const double* true
  * every sample has finished are device-side no-ops (the reference returns early, :239). */
 int icnn_solve_batch_fused(const icnn_picnn_t* h, const icnn_gates* gates, const icnn_bundle_cfg* cfg,
                            const icnn_bundle_bufs* b, void* workspace, void* stream);
+/* The same loop as a CUDA graph ("CUDA graph or persistent kernel"): the
+ * reference crosses host<->device once per iteration (lib/bundle_entropy.py:204-205); here the
+ * 2 + nIter*(2L+3) launches of icnn_solve_batch_fused are captured ONCE and replayed with a single
+ * cudaGraphLaunch per solveBatch.  create() captures on a private stream (nothing executes); every device
+ * pointer reachable from (h, gates, b, workspace) and the values of cfg are baked in, so launch() is only
+ * valid while those buffers are alive and at the same addresses (the Python layer keys its cache on them).
+ * nodes() = kernel nodes in the graph (= gpu launches replayed per call). */
+typedef struct icnn_loop_graph icnn_loop_graph_t;
+int icnn_loop_graph_create(const icnn_picnn_t* h, const icnn_gates* gates, const icnn_bundle_cfg* cfg,
+                           const icnn_bundle_bufs* b, void* workspace, icnn_loop_graph_t** out);
+int icnn_loop_graph_launch(icnn_loop_graph_t* g, void* stream);
+int64_t icnn_loop_graph_nodes(const icnn_loop_graph_t* g);
+int icnn_loop_graph_destroy(icnn_loop_graph_t* g);
 /* replaces: the unrolled momentum-GD inner loop, multi-label-cls/icnn-back.py:116-131
  * (= completion/icnn.back.py:133-147).  y32 [B,n] in/out, v [B,n] scratch, f_out [B] = f(y_n). */
 int icnn_gd_solve(const icnn_picnn_t* h, const icnn_gates* gates, float* y32, float* v, float* g,

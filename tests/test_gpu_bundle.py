@@ -476,6 +476,66 @@ def test_resident_cluster_variant_matches_streaming(name, B, nIter, env, monkeyp
     assert rowdiff(ref[0], alt[0])[same].max() < 1e-9
 
 
+@pytest.mark.parametrize("name,B,nIter,env_ref,env_alt", [
+    ("C5", 3, 12, {"ICNN_PC_V3": "0"}, {}),                  # n_y = 4096: three-vector build is the default
+    ("C5", 3, 45, {"ICNN_PC_V3": "0"}, {}),                  # deep horizon: k up to ~35 rows, every row-block shape of sweep A
+    ("C2", 5, 14, {}, {"ICNN_PC_V3": "1"}),                  # n_y = 2048: forced three-vector build vs the five-sweep default
+])
+def test_three_vector_pc_kernel_matches_four_vector(name, B, nIter, env_ref, env_alt, monkeypatch):
+    """The V3 build of the predictor-corrector kernel (y, ry, du in shared memory; u = ry - logit(y) and dy recomputed
+    in the update; two samples per SM at n_y = 4096) walks the same interior-point iterates as the four-vector build
+    up to FP64 rounding of the recovered u."""
+    from icnn_b200 import bundle_entropy as be
+    p, x, y0 = synth.make_inputs(name, B=B)
+    fg = r32(picnn_np.make_fg(p, x))
+    for k_, v_ in env_ref.items():
+        monkeypatch.setenv(k_, v_)
+    ref = be.solveBatch(fg, y0.copy(), nIter=nIter)
+    for k_ in env_ref:
+        monkeypatch.delenv(k_)
+    for k_, v_ in env_alt.items():
+        monkeypatch.setenv(k_, v_)
+    alt = be.solveBatch(fg, y0.copy(), nIter=nIter)
+    same = (lens(ref[1]) == lens(alt[1])) & (np.array(ref[5]) == np.array(alt[5]))
+    assert same.mean() >= 0.6
+    assert rowdiff(ref[0], alt[0])[same].max() < 1e-9
+    assert np.all((alt[0] > 0) & (alt[0] < 1))
+
+
+def test_loop_graph_replays_the_fused_loop_bit_for_bit():
+    """solveBatch(graph=True): the nIter x (K1, K2) launches captured once into a CUDA graph (icnn_loop_graph_*)
+    and replayed with one launch give the same bits as the eager enqueue, call after call; the capture is keyed on
+    the buffers it bakes in (a new bind -> a new capture, never a stale replay)."""
+    import icnn_b200
+    from icnn_b200 import _capi, bundle_entropy as be
+    for name, B, nIter in (("C3", 48, 6), ("C4", 300, 5), ("T", 70, 5)):
+        cfg = synth.CONFIGS[name]
+        p, x, y0 = synth.make_inputs(name, B=B)
+        net = icnn_b200.PICNN.from_params(p)
+        fgd = net.bind(x, affine=cfg["affine"])
+        kw = dict(nIter=nIter, variant=cfg["variant"])
+        r0 = be.solveBatch(fgd, y0.copy(), return_state=True, **kw)
+        st = r0[-1]
+        g1 = be.solveBatch(fgd, y0.copy(), state=st, graph=True, **kw)
+        assert len(st._graphs) == 1
+        nodes = _capi.lib.icnn_loop_graph_nodes(next(iter(st._graphs.values())))
+        assert nodes >= 2 * nIter + 1
+        g2 = be.solveBatch(fgd, y0.copy(), state=st, graph=True, **kw)      # replay
+        assert len(st._graphs) == 1
+        assert np.array_equal(r0[0], g1[0]) and np.array_equal(r0[0], g2[0])
+        assert r0[5] == g1[5] == g2[5]
+        # other inputs through the same captured graph: the graph reads y0 / the gates from the baked-in buffers
+        y1 = np.clip(y0 + 0.05, 0.01, 0.99)
+        e1 = be.solveBatch(fgd, y1.copy(), **kw)
+        g3 = be.solveBatch(fgd, y1.copy(), state=st, graph=True, **kw)
+        assert np.array_equal(e1[0], g3[0])
+        # a second bind has its own gate buffers -> its own capture
+        fgd2 = net.bind(x[::-1].copy(), affine=cfg["affine"])
+        e2 = be.solveBatch(fgd2, y0.copy(), **kw)
+        g4 = be.solveBatch(fgd2, y0.copy(), state=st, graph=True, **kw)
+        assert np.array_equal(e2[0], g4[0])
+
+
 @pytest.mark.parametrize("name,B,nIter,variant", [("C1", 64, 5, "lib"), ("C1", 64, 8, "dual"), ("C4", 300, 5, "rl")])
 def test_thread_per_sample_kernel_matches_group_kernel(name, B, nIter, variant, monkeypatch):
     """n_y <= 8 runs the one-thread-per-sample K2 (bundle_step_small.cu); ICNN_K2_SMALL=0 forces the
