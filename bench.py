@@ -649,7 +649,7 @@ def run_gpu(args):
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches_per_step"] * args.steps,
             "clocks": head.get("clocks"), "roofline": head["roofline"], "kernels": head["kernels"],
             "cpu_baseline": head.get("cpu_baseline"), "e2e_over_cpu": head.get("e2e_over_cpu"),
-            "per_iteration": head["per_iteration"],
+            "per_iteration": head["per_iteration"], "loop_graph": head.get("loop_graph"),
             "fp64_mma_peak_tflops": ctx.fp64_peak,
             "configs": subs,
             "target_shape": subs.get("T"),

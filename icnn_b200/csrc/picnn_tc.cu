@@ -137,11 +137,13 @@ __device__ __forceinline__ float tf32_lo(float x, float hi) { return tf32_rn(x -
 // ---------------------------------------------------------------------------------------------
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;  // fp32 elements per stage row = one 128-byte swizzle span
-constexpr int TC_CH = 1;   // k-blocks per accumulation chunk (K = 32: four accumulations per TMEM accumulator before the RN drain)
+constexpr int TC_CH = 1;   // default k-blocks per accumulation chunk (K = 32: four accumulations per TMEM accumulator before the RN
+                           // drain); TcArgs::ch carries the value a launch uses (ICNN_TC_CH, read once: accuracy/speed exploration)
 constexpr int TC_SETS = 3; // hi*hi accumulators in flight (+ one cross-term accumulator = 4 x BN TMEM columns)
 
 struct TcArgs {
   int M, N, K;
+  int ch;    // k-blocks per accumulation chunk (>= 1), set by launch_tc_gemm
   int mode;  // 0 forward, 1 backward, 2 plain store (self test)
   // forward epilogue: Z = act(acc + D); optional next-layer operand A'_{next}[:, 0:N] = Z o Cz_next (hi/lo)
   const float* D; float* Z; float alpha;
@@ -241,14 +243,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
-      const int nch = (nkb + TC_CH - 1) / TC_CH;
+      const int CH = a.ch;
+      const int nch = (nkb + CH - 1) / CH;
       const uint32_t xx = tmem_base + (uint32_t)(TC_SETS * BN);
       for (int c = 0; c < nch; ++c) {
         const int set = c % TC_SETS;
         if (c >= TC_SETS) { mbar_wait(&acc_empty[set], (uint32_t)(((c / TC_SETS) - 1) & 1)); tc_fence_after(); }
         const uint32_t hh = tmem_base + (uint32_t)(set * BN);
-        const int kb1 = ::min(nkb, (c + 1) * TC_CH);
-        for (int kb = c * TC_CH; kb < kb1; ++kb) {
+        const int kb1 = ::min(nkb, (c + 1) * CH);
+        for (int kb = c * CH; kb < kb1; ++kb) {
           const int s = kb % SM::NST;
           const uint32_t ph = (kb / SM::NST) & 1;
           mbar_wait(&full[s], ph);
@@ -261,7 +264,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
           for (int k4 = 0; k4 < TC_BK / 8; ++k4) {
             const uint64_t adv = (uint64_t)((k4 * 8 * 4) >> 4);  // +32 B per k-step inside the swizzle span
-            const uint32_t first = (kb == c * TC_CH && k4 == 0) ? 0u : 1u;
+            const uint32_t first = (kb == c * CH && k4 == 0) ? 0u : 1u;
             umma_tf32(hh, dAh + adv, dBh + adv, idesc, first);
             umma_tf32(xx, dAh + adv, dBl + adv, idesc, (kb == 0 && k4 == 0) ? 0u : 1u);
             umma_tf32(xx, dAl + adv, dBh + adv, idesc, 1u);
@@ -283,7 +286,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
     for (int j = 0; j < BN; ++j) run[j] = 0.f;
     {
-      const int nch = (nkb + TC_CH - 1) / TC_CH;
+      const int nch = (nkb + a.ch - 1) / a.ch;
       for (int c = 0; c < nch; ++c) {
         const int set = c % TC_SETS;
         mbar_wait(&acc_full[set], (uint32_t)((c / TC_SETS) & 1));
@@ -659,6 +662,12 @@ static int launch_tc_gemm(const float* Ah, const float* Al, long long lda, const
     const int w = v ? atoi(v) : 0;
     return (w == 1 || w == 2 || w == 4 || w == 8) ? w : 0;
   }();
+  static const int env_ch = [] {
+    const char* v = getenv("ICNN_TC_CH");
+    const int w = v ? atoi(v) : 0;
+    return (w >= 1 && w <= 64) ? w : TC_CH;
+  }();
+  a.ch = env_ch;
   if (env_cfg >= 0) cfg = env_cfg;
   if (gdb && cfg == 0) cfg = 1;
   const int BN = cfg == 0 ? 128 : 64;
