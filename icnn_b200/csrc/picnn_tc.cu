@@ -62,6 +62,18 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, ui
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// one lane of a converged warp, chosen by the hardware (elect.sync): unlike `lane == 0`, ptxas knows that exactly one
+// thread runs the guarded region, so single-thread instructions (tcgen05.mma / commit, cp.async.bulk.tensor) are
+// emitted straight instead of inside an ELECT / BRA.U.ANY loop over the active lanes
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -187,7 +199,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   if (a.skip_if_zero != nullptr && *a.skip_if_zero == 0) return;
   using SM = TcSmem<BN, NST_>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment (128B swizzle atoms) as an OFFSET into the shared array: a pointer rebuilt from an integer
+  // (uintptr_t round-up) loses its address space, the read of the TMEM base address below becomes a GENERIC load,
+  // which the compiler must treat as lane-divergent -- and every tcgen05.mma then gets an ELECT / R2UR.BROADCAST /
+  // BRA.U.ANY "waterfall" around it (13 SASS instructions per MMA; ncu, round 2: the single MMA-issuing thread never
+  // waited on a barrier and the tensor pipe sat at 23-28 %: the kernel was bound by that thread's instruction stream).
+  const uint32_t smem_pad = ((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + smem_pad;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
   uint64_t* empty = full + SM::NST;
   uint64_t* acc_full = empty + SM::NST;           // [TC_SETS] hi*hi accumulator s holds a finished chunk
@@ -225,7 +243,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % SM::NST;
         const uint32_t ph = (kb / SM::NST) & 1;
@@ -241,7 +259,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
       const int CH = a.ch;
       const int nch = (nkb + CH - 1) / CH;
