@@ -66,7 +66,12 @@ __device__ __forceinline__ double chol_dot(const double* a, const double* b, int
   for (; p < c; ++p) t0 = fma(a[p], b[p], t0);
   return (t0 + t1) + (t2 + t3);
 }
-__device__ inline bool warp_cholesky_p(double* L, double* invd, int k, int lane) {
+// K32: k <= 32 -> lane r owns row r only; the second-row paths (r + 32) and the (i < 32) selects compile away.
+// The one-warp k x k stage is latency- AND issue-bound (ncu, C5: 9.2k warp instructions per stage at k = 20, IPC 0.27,
+// a quarter of the kernel's time with the other warps parked at the barrier behind it), so the common k <= 32 case
+// gets its own lean instantiation.
+template <bool K32>
+__device__ __forceinline__ bool warp_cholesky_impl(double* L, double* invd, int k, int lane) {
   bool ok = true;
   const int r0 = lane, r1 = lane + 32;
   const int o0 = lidx(r0, 0), o1 = lidx(r1, 0);
@@ -74,48 +79,57 @@ __device__ inline bool warp_cholesky_p(double* L, double* invd, int k, int lane)
     const int oc = lidx(c, 0);
     double s0 = 0.0, s1 = 0.0;
     if (r0 >= c && r0 < k) s0 = L[o0 + c] - chol_dot(L + o0, L + oc, c);
-    if (r1 >= c && r1 < k) s1 = L[o1 + c] - chol_dot(L + o1, L + oc, c);
-    const double piv = __shfl_sync(0xffffffffu, (c < 32) ? s0 : s1, c & 31);
+    if (!K32) { if (r1 >= c && r1 < k) s1 = L[o1 + c] - chol_dot(L + o1, L + oc, c); }
+    const double piv = K32 ? __shfl_sync(0xffffffffu, s0, c) : __shfl_sync(0xffffffffu, (c < 32) ? s0 : s1, c & 31);
     if (!(piv > 0.0) || !isfinite(piv)) { ok = false; break; }
     const double inv = rsqrt(piv);
     if (r0 > c && r0 < k) L[o0 + c] = s0 * inv;
-    if (r1 > c && r1 < k) L[o1 + c] = s1 * inv;
+    if (!K32) { if (r1 > c && r1 < k) L[o1 + c] = s1 * inv; }
     if (lane == 0) { L[oc + c] = piv * inv; invd[c] = inv; }
     __syncwarp();
   }
   __syncwarp();
   return ok;
 }
+__device__ inline bool warp_cholesky_p(double* L, double* invd, int k, int lane) {
+  return k <= 32 ? warp_cholesky_impl<true>(L, invd, k, lane) : warp_cholesky_impl<false>(L, invd, k, lane);
+}
 
 // L L^T X = B for NR right-hand sides held in registers (lane r owns rows r, r + 32), pivots by shuffle.
-template <int NR>
-__device__ inline void warp_chol_solve_p(const double* L, const double* invd, int k, double (&b0)[NR],
-                                         double (&b1)[NR], int lane) {
+template <int NR, bool K32>
+__device__ __forceinline__ void warp_chol_solve_impl(const double* L, const double* invd, int k, double (&b0)[NR],
+                                                     double (&b1)[NR], int lane) {
   const int r0 = lane, r1 = lane + 32;
   const int o0 = lidx(r0, 0), o1 = lidx(r1, 0);
   for (int i = 0; i < k; ++i) {
     const double di = invd[i];
     const double l0 = (r0 > i && r0 < k) ? L[o0 + i] : 0.0;
-    const double l1 = (r1 > i && r1 < k) ? L[o1 + i] : 0.0;
+    const double l1 = (!K32 && r1 > i && r1 < k) ? L[o1 + i] : 0.0;
 #pragma unroll
     for (int q = 0; q < NR; ++q) {
-      const double xi = __shfl_sync(0xffffffffu, (i < 32) ? b0[q] : b1[q], i & 31) * di;
+      const double xi = (K32 ? __shfl_sync(0xffffffffu, b0[q], i) : __shfl_sync(0xffffffffu, (i < 32) ? b0[q] : b1[q], i & 31)) * di;
       b0[q] = (r0 == i) ? xi : fma(-l0, xi, b0[q]);
-      b1[q] = (r1 == i) ? xi : fma(-l1, xi, b1[q]);
+      if (!K32) b1[q] = (r1 == i) ? xi : fma(-l1, xi, b1[q]);
     }
   }
   for (int i = k - 1; i >= 0; --i) {
     const double di = invd[i];
     const int oi = lidx(i, 0);
     const double l0 = (r0 < i) ? L[oi + r0] : 0.0;
-    const double l1 = (r1 < i) ? L[oi + r1] : 0.0;
+    const double l1 = (!K32 && r1 < i) ? L[oi + r1] : 0.0;
 #pragma unroll
     for (int q = 0; q < NR; ++q) {
-      const double xi = __shfl_sync(0xffffffffu, (i < 32) ? b0[q] : b1[q], i & 31) * di;
+      const double xi = (K32 ? __shfl_sync(0xffffffffu, b0[q], i) : __shfl_sync(0xffffffffu, (i < 32) ? b0[q] : b1[q], i & 31)) * di;
       b0[q] = (r0 == i) ? xi : fma(-l0, xi, b0[q]);
-      b1[q] = (r1 == i) ? xi : fma(-l1, xi, b1[q]);
+      if (!K32) b1[q] = (r1 == i) ? xi : fma(-l1, xi, b1[q]);
     }
   }
+}
+template <int NR>
+__device__ inline void warp_chol_solve_p(const double* L, const double* invd, int k, double (&b0)[NR],
+                                         double (&b1)[NR], int lane) {
+  if (k <= 32) warp_chol_solve_impl<NR, true>(L, invd, k, b0, b1, lane);
+  else warp_chol_solve_impl<NR, false>(L, invd, k, b0, b1, lane);
 }
 
 // get_step (lib/bundle_entropy.py:158-163) over a k-vector whose elements j = lane, lane + 32 sit in registers
@@ -410,6 +424,60 @@ __device__ __forceinline__ void ratio_min(double& nm, double& dn, double a, doub
   if (a * dn < nm * b) { nm = a; dn = b; }
 }
 
+// ---- k x k stage (one warp): rd, stopping test, Cholesky of M = M0 + diag(s/z), the four solves ------------------
+// K32: k <= 32, every lane owns at most one element / row (the j + 32 halves compile away).
+struct PcKxk {
+  double* Lp; double* invd; const double* zc; const double* scur; const double* wk; const double* hk; const double* qk;
+  double* dza; double* dzp; double* dzq; double* dsa; double* sc; int* isc;
+};
+template <bool K32>
+__device__ __forceinline__ void pc_kxk_stage(const PcKxk& io, int k, int lane, double pr) {
+  double* Lp = io.Lp;
+  const int j0 = lane, j1 = lane + 32;
+  const bool v0 = j0 < k, v1ok = !K32 && j1 < k;
+  const double tt = io.sc[0];
+  const double z0 = v0 ? io.zc[j0] : 0.0, z1 = v1ok ? io.zc[j1] : 0.0;
+  const double s0 = v0 ? io.scur[j0] : 0.0, s1 = v1ok ? io.scur[j1] : 0.0;
+  const double rd0 = v0 ? ((io.wk[j0] + io.hk[j0]) - tt) + s0 : 0.0;    // rd = G y + h - t + s
+  const double rd1 = v1ok ? ((io.wk[j1] + io.hk[j1]) - tt) + s1 : 0.0;
+  const double zs = Grp<1>::wsum(z0 + z1);
+  const double dr = Grp<1>::wsum(fma(rd0, rd0, rd1 * rd1));
+  const double rt = 1.0 - zs;
+  const bool conv = (sqrt(pr + rt * rt) < 1e-8 && sqrt(dr) < 1e-8);
+  if (conv) {
+    if (lane == 0) io.isc[2] = 1;
+  } else {
+    if (v0) Lp[lidx(j0, j0)] += s0 / z0;
+    if (v1ok) Lp[lidx(j1, j1)] += s1 / z1;
+    __syncwarp();
+    const bool ok = warp_cholesky_impl<K32>(Lp, io.invd, k, lane);
+    if (!ok) { if (lane == 0) io.isc[3] = 1; }
+    else {
+      const double mu = Grp<1>::wsum(fma(s0, z0, s1 * z1)) / k;
+      // three right-hand sides in one sweep: 1, r_aff = rd - G D ry - s  (rc = z), mu / z
+      const double ra0 = v0 ? rd0 - io.qk[j0] - s0 : 0.0, ra1 = v1ok ? rd1 - io.qk[j1] - s1 : 0.0;
+      const double rp0 = v0 ? mu / z0 : 0.0, rp1 = v1ok ? mu / z1 : 0.0;
+      double b0[3] = {v0 ? 1.0 : 0.0, ra0, rp0}, b1[3] = {v1ok ? 1.0 : 0.0, ra1, rp1};
+      warp_chol_solve_impl<3, K32>(Lp, io.invd, k, b0, b1, lane);
+      const double w1s = Grp<1>::wsum(b0[0] + b1[0]);
+      const double dta = (Grp<1>::wsum(fma(ra0, b0[0], ra1 * b1[0])) - rt) / w1s;
+      const double dtp = Grp<1>::wsum(fma(rp0, b0[0], rp1 * b1[0])) / w1s;
+      const double da0 = fma(-dta, b0[0], b0[1]), da1 = fma(-dta, b1[0], b1[1]);   // dz_aff
+      const double dp0 = fma(-dtp, b0[0], b0[2]), dp1 = fma(-dtp, b1[0], b1[2]);   // dz_p
+      const double dsa0 = v0 ? -(s0 / z0) * (z0 + da0) : 0.0, dsa1 = v1ok ? -(s1 / z1) * (z1 + da1) : 0.0;
+      // r_q = -(ds_aff o dz_aff) / z
+      const double rq0 = v0 ? -(dsa0 * da0) / z0 : 0.0, rq1 = v1ok ? -(dsa1 * da1) / z1 : 0.0;
+      double c0[1] = {rq0}, c1[1] = {rq1};
+      warp_chol_solve_impl<1, K32>(Lp, io.invd, k, c0, c1, lane);
+      const double dtq = Grp<1>::wsum(fma(rq0, b0[0], rq1 * b1[0])) / w1s;
+      if (v0) { io.dza[j0] = da0; io.dzp[j0] = dp0; io.dzq[j0] = fma(-dtq, b0[0], c0[0]); io.dsa[j0] = dsa0; }
+      if (v1ok) { io.dza[j1] = da1; io.dzp[j1] = dp1; io.dzq[j1] = fma(-dtq, b1[0], c1[0]); io.dsa[j1] = dsa1; }
+      if (lane == 0) { io.sc[1] = dta; io.sc[2] = dtp; io.sc[3] = dtq; }
+    }
+  }
+  __syncwarp();
+}
+
 // ---- the kernel ----------------------------------------------------------------------------------------
 // One CTA of WPS warps per sample (the block scheduler balances the SMs at sample granularity: with several
 // samples per CTA the last, partly filled wave costs a whole extra round);  NCH = chunks of 4 T columns per
@@ -494,7 +562,7 @@ __global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WP
       hs = fma(ge, ye, hs);
       rs += ge;
       if (!isfinite(ge)) bad = 1.0;
-      if (ysrow) ysrow[e] = ye;
+      if (ysrow) __stcs(ysrow + e, ye);   // write-only during the solve: streaming store, keeps the bundle rows in L2
       if (b.iter_stats) ent += neg_entropy(ye);
     }
     if (b.iter_stats) ent = g.sum(ent);
@@ -634,48 +702,9 @@ __global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WP
     gram_pass_pc<WPS, VEC, GV>(g, rowp, k, n, yv, rv, Lp, qk, wk, xv, npad);
     // ---- k x k stage
     if (g.warp == 0) {
-      const int lane = g.lane;
-      const double tt = sc[0];
-      const double z0 = v0 ? zc[j0] : 0.0, z1 = v1ok ? zc[j1] : 0.0;
-      const double s0 = v0 ? scur[j0] : 0.0, s1 = v1ok ? scur[j1] : 0.0;
-      const double rd0 = v0 ? ((wk[j0] + hk[j0]) - tt) + s0 : 0.0;    // rd = G y + h - t + s
-      const double rd1 = v1ok ? ((wk[j1] + hk[j1]) - tt) + s1 : 0.0;
-      const double zs = Grp<1>::wsum(z0 + z1);
-      const double dr = Grp<1>::wsum(fma(rd0, rd0, rd1 * rd1));
-      const double rt = 1.0 - zs;
-      const bool conv = (sqrt(pr + rt * rt) < 1e-8 && sqrt(dr) < 1e-8);
-      if (conv) {
-        if (lane == 0) isc[2] = 1;
-      } else {
-        if (v0) Lp[lidx(j0, j0)] += s0 / z0;
-        if (v1ok) Lp[lidx(j1, j1)] += s1 / z1;
-        __syncwarp();
-        const bool ok = warp_cholesky_p(Lp, invd, k, lane);
-        if (!ok) { if (lane == 0) isc[3] = 1; }
-        else {
-          const double mu = Grp<1>::wsum(fma(s0, z0, s1 * z1)) / k;
-          // three right-hand sides in one sweep: 1, r_aff = rd - G D ry - s  (rc = z), mu / z
-          const double ra0 = v0 ? rd0 - qk[j0] - s0 : 0.0, ra1 = v1ok ? rd1 - qk[j1] - s1 : 0.0;
-          const double rp0 = v0 ? mu / z0 : 0.0, rp1 = v1ok ? mu / z1 : 0.0;
-          double b0[3] = {v0 ? 1.0 : 0.0, ra0, rp0}, b1[3] = {v1ok ? 1.0 : 0.0, ra1, rp1};
-          warp_chol_solve_p<3>(Lp, invd, k, b0, b1, lane);
-          const double w1s = Grp<1>::wsum(b0[0] + b1[0]);
-          const double dta = (Grp<1>::wsum(fma(ra0, b0[0], ra1 * b1[0])) - rt) / w1s;
-          const double dtp = Grp<1>::wsum(fma(rp0, b0[0], rp1 * b1[0])) / w1s;
-          const double da0 = fma(-dta, b0[0], b0[1]), da1 = fma(-dta, b1[0], b1[1]);   // dz_aff
-          const double dp0 = fma(-dtp, b0[0], b0[2]), dp1 = fma(-dtp, b1[0], b1[2]);   // dz_p
-          const double dsa0 = v0 ? -(s0 / z0) * (z0 + da0) : 0.0, dsa1 = v1ok ? -(s1 / z1) * (z1 + da1) : 0.0;
-          // r_q = -(ds_aff o dz_aff) / z
-          const double rq0 = v0 ? -(dsa0 * da0) / z0 : 0.0, rq1 = v1ok ? -(dsa1 * da1) / z1 : 0.0;
-          double c0[1] = {rq0}, c1[1] = {rq1};
-          warp_chol_solve_p<1>(Lp, invd, k, c0, c1, lane);
-          const double dtq = Grp<1>::wsum(fma(rq0, b0[0], rq1 * b1[0])) / w1s;
-          if (v0) { dza[j0] = da0; dzp[j0] = dp0; dzq[j0] = fma(-dtq, b0[0], c0[0]); dsa[j0] = dsa0; }
-          if (v1ok) { dza[j1] = da1; dzp[j1] = dp1; dzq[j1] = fma(-dtq, b1[0], c1[0]); dsa[j1] = dsa1; }
-          if (lane == 0) { sc[1] = dta; sc[2] = dtp; sc[3] = dtq; }
-        }
-      }
-      __syncwarp();
+      const PcKxk io{Lp, invd, zc, scur, wk, hk, qk, dza, dzp, dzq, dsa, sc, isc};
+      if (k <= 32) pc_kxk_stage<true>(io, k, g.lane, pr);
+      else pc_kxk_stage<false>(io, k, g.lane, pr);
     }
     g.sync();
     if (isc[2]) break;

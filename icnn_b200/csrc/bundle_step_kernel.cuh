@@ -173,7 +173,10 @@ struct Grp {
 // In-place lower Cholesky of the symmetric matrix A (full storage, leading dim ld), left-looking,
 // lane r owns rows r and r+32.  invd[c] = 1 / L[c][c].  Returns false on a non-positive /
 // non-finite pivot.  One __syncwarp per column; pivots travel by shuffle, not shared memory.
-__device__ inline bool warp_cholesky(double* A, double* invd, int k, int ld, int lane) {
+// K32 (k <= 32): lane r owns row r only -- the r + 32 halves and the (c < 32) selects compile away (this one-warp
+// stage is issue-bound: ncu counted 460 warp instructions per row of k in the general form).
+template <bool K32>
+__device__ __forceinline__ bool warp_cholesky_t(double* A, double* invd, int k, int ld, int lane) {
   bool ok = true;
   const int r0 = lane, r1 = lane + 32;
   for (int c = 0; c < k; ++c) {
@@ -182,64 +185,75 @@ __device__ inline bool warp_cholesky(double* A, double* invd, int k, int ld, int
       s0 = A[r0 * ld + c];
       for (int p = 0; p < c; ++p) s0 = fma(-A[r0 * ld + p], A[c * ld + p], s0);
     }
-    if (r1 >= c && r1 < k) {
-      s1 = A[r1 * ld + c];
-      for (int p = 0; p < c; ++p) s1 = fma(-A[r1 * ld + p], A[c * ld + p], s1);
+    if (!K32) {
+      if (r1 >= c && r1 < k) {
+        s1 = A[r1 * ld + c];
+        for (int p = 0; p < c; ++p) s1 = fma(-A[r1 * ld + p], A[c * ld + p], s1);
+      }
     }
-    const double piv = __shfl_sync(0xffffffffu, (c < 32) ? s0 : s1, c & 31);
+    const double piv = K32 ? __shfl_sync(0xffffffffu, s0, c) : __shfl_sync(0xffffffffu, (c < 32) ? s0 : s1, c & 31);
     if (!(piv > 0.0) || !isfinite(piv)) { ok = false; break; }
     const double inv = rsqrt(piv);
     if (r0 > c && r0 < k) A[r0 * ld + c] = s0 * inv;
-    if (r1 > c && r1 < k) A[r1 * ld + c] = s1 * inv;
+    if (!K32) { if (r1 > c && r1 < k) A[r1 * ld + c] = s1 * inv; }
     if (lane == 0) { A[c * ld + c] = piv * inv; invd[c] = inv; }
     __syncwarp();
   }
   __syncwarp();
   return ok;
 }
+__device__ inline bool warp_cholesky(double* A, double* invd, int k, int ld, int lane) {
+  return k <= 32 ? warp_cholesky_t<true>(A, invd, k, ld, lane) : warp_cholesky_t<false>(A, invd, k, ld, lane);
+}
 
 // Solve L L^T X = B in place for NR right-hand sides held in shared memory (rhs[q][0..k)).
 // The running vectors live in registers (lane r owns rows r, r+32) and the pivots are broadcast
 // by shuffle, so a substitution step costs one shuffle + one FMA of latency instead of two
 // shared-memory round trips.
-template <int NR>
-__device__ inline void warp_chol_solve(const double* L, const double* invd, int k, int ld,
-                                       double* const (&rhs)[NR], int lane) {
+template <int NR, bool K32>
+__device__ __forceinline__ void warp_chol_solve_t(const double* L, const double* invd, int k, int ld,
+                                                  double* const (&rhs)[NR], int lane) {
   const int r0 = lane, r1 = lane + 32;
   double b0[NR], b1[NR];
 #pragma unroll
   for (int q = 0; q < NR; ++q) {
     b0[q] = (r0 < k) ? rhs[q][r0] : 0.0;
-    b1[q] = (r1 < k) ? rhs[q][r1] : 0.0;
+    b1[q] = (!K32 && r1 < k) ? rhs[q][r1] : 0.0;
   }
   for (int i = 0; i < k; ++i) {  // forward: L x = b
     const double di = invd[i];
     const double l0 = (r0 > i && r0 < k) ? L[r0 * ld + i] : 0.0;
-    const double l1 = (r1 > i && r1 < k) ? L[r1 * ld + i] : 0.0;
+    const double l1 = (!K32 && r1 > i && r1 < k) ? L[r1 * ld + i] : 0.0;
 #pragma unroll
     for (int q = 0; q < NR; ++q) {
-      const double xi = __shfl_sync(0xffffffffu, (i < 32) ? b0[q] : b1[q], i & 31) * di;
+      const double xi = (K32 ? __shfl_sync(0xffffffffu, b0[q], i) : __shfl_sync(0xffffffffu, (i < 32) ? b0[q] : b1[q], i & 31)) * di;
       b0[q] = (r0 == i) ? xi : fma(-l0, xi, b0[q]);
-      b1[q] = (r1 == i) ? xi : fma(-l1, xi, b1[q]);
+      if (!K32) b1[q] = (r1 == i) ? xi : fma(-l1, xi, b1[q]);
     }
   }
   for (int i = k - 1; i >= 0; --i) {  // backward: L^T x = b
     const double di = invd[i];
     const double l0 = (r0 < i) ? L[i * ld + r0] : 0.0;
-    const double l1 = (r1 < i) ? L[i * ld + r1] : 0.0;
+    const double l1 = (!K32 && r1 < i) ? L[i * ld + r1] : 0.0;
 #pragma unroll
     for (int q = 0; q < NR; ++q) {
-      const double xi = __shfl_sync(0xffffffffu, (i < 32) ? b0[q] : b1[q], i & 31) * di;
+      const double xi = (K32 ? __shfl_sync(0xffffffffu, b0[q], i) : __shfl_sync(0xffffffffu, (i < 32) ? b0[q] : b1[q], i & 31)) * di;
       b0[q] = (r0 == i) ? xi : fma(-l0, xi, b0[q]);
-      b1[q] = (r1 == i) ? xi : fma(-l1, xi, b1[q]);
+      if (!K32) b1[q] = (r1 == i) ? xi : fma(-l1, xi, b1[q]);
     }
   }
 #pragma unroll
   for (int q = 0; q < NR; ++q) {
     if (r0 < k) rhs[q][r0] = b0[q];
-    if (r1 < k) rhs[q][r1] = b1[q];
+    if (!K32) { if (r1 < k) rhs[q][r1] = b1[q]; }
   }
   __syncwarp();
+}
+template <int NR>
+__device__ inline void warp_chol_solve(const double* L, const double* invd, int k, int ld,
+                                       double* const (&rhs)[NR], int lane) {
+  if (k <= 32) warp_chol_solve_t<NR, true>(L, invd, k, ld, rhs, lane);
+  else warp_chol_solve_t<NR, false>(L, invd, k, ld, rhs, lane);
 }
 
 // step length keeping v + a dv >= 0  (lib/bundle_entropy.py:158-163), over a k-vector, one warp
@@ -580,7 +594,7 @@ __global__ void __launch_bounds__(WPS == 16 ? 512 : 256, MINB) bundle_step_kerne
       hs = fma(ge, ye, hs);
       rs += ge;
       if (!isfinite(ge)) bad = 1.0;
-      if (ysrow) ysrow[e] = ye;
+      if (ysrow) __stcs(ysrow + e, ye);   // write-only during the solve: streaming store, keeps the bundle rows in L2
       if (b.iter_stats) ent += neg_entropy(ye);
     }
     if (b.iter_stats) ent = g.csum(ent);
