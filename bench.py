@@ -501,7 +501,7 @@ def measure_workload(ctx, name, steps, warmup, scaling, solver, cpu_seconds, hea
     k2_name = ("bundle_step_small_kernel (one thread per sample)" if small else
                "bundle_pc_kernel<8 warps, three n-vectors> (two-sweep PC, DMMA; two samples per SM)"
                if (solver == "pc" and variant == "lib" and 2048 < n <= 4096 and n % 4 == 0 and os.environ.get("ICNN_PC_V3", "") != "0")
-               else "bundle_pc_kernel (two-sweep PC, DMMA)" if (solver == "pc" and variant == "lib" and (n <= 256 or n > 2048))
+               else "bundle_pc_kernel (two-sweep PC, DMMA)" if (solver == "pc" and variant == "lib" and (n <= 256 or n > 1024))
                else "bundle_step_kernel (DMMA Gram, FP64)")
     # K2: bound by the FP64 pipe (DMMA Gram + FP64 vector work); SURVEY.md 8d's HBM model kept beside it
     k2_flops = k2_fp64_flops(n, stats)

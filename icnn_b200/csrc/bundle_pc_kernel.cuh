@@ -37,6 +37,7 @@ struct PcArgs {
   icnn_bundle_cfg c;
   int t;
   int npad;  // doubles reserved per n-vector
+  int flags; // exploration knobs (bundle_pc.cu): bit 0 = general k x k stage even for k <= 32, bit 1 = plain stores for xs
 };
 
 constexpr int PC_NKV = 18;
@@ -562,7 +563,7 @@ __global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WP
       hs = fma(ge, ye, hs);
       rs += ge;
       if (!isfinite(ge)) bad = 1.0;
-      if (ysrow) __stcs(ysrow + e, ye);   // write-only during the solve: streaming store, keeps the bundle rows in L2
+      if (ysrow) { if (A.flags & 2) ysrow[e] = ye; else __stcs(ysrow + e, ye); }   // write-only during the solve: streaming store
       if (b.iter_stats) ent += neg_entropy(ye);
     }
     if (b.iter_stats) ent = g.sum(ent);
@@ -703,7 +704,7 @@ __global__ void __launch_bounds__(WPS * 32, WPS == 16 ? 1 : (R80 ? 24 : 16) / WP
     // ---- k x k stage
     if (g.warp == 0) {
       const PcKxk io{Lp, invd, zc, scur, wk, hk, qk, dza, dzp, dzq, dsa, sc, isc};
-      if (k <= 32) pc_kxk_stage<true>(io, k, g.lane, pr);
+      if (k <= 32 && !(A.flags & 1)) pc_kxk_stage<true>(io, k, g.lane, pr);
       else pc_kxk_stage<false>(io, k, g.lane, pr);
     }
     g.sync();
