@@ -6,9 +6,12 @@ What the reference computes: ``opt.compute_gradients(self.mse_, self.theta_)`` o
 unrolls ``nIter`` momentum-GD steps on the energy (multi-label-cls/icnn-back.py:120-139 =
 completion/icnn.back.py:133-156), i.e. TensorFlow double-backprop through
 ``tf.gradients(Ei_, yi_)``.  TensorFlow is absent here, so this file restates the result
-analytically and is pinned by torch autograd (float64, ``create_graph=True``) on the same unrolled
-graph (tests/test_oracle_gd_grad.py, oracle/gen_golden_gd_grad.py): **parity unpinned by reference
-execution**, pinned against an independent autodiff of the same recurrence.
+analytically.  Pins (tests/test_oracle_gd_grad.py, tests/test_oracle_tfshim.py): (i) the reference's own
+``Model.__init__`` / ``Model.f`` of multi-label-cls/icnn-back.py, unmodified, executed on the TF-primitive
+stand-in oracle/tf_shim.py -- ``yn_``, ``mse_`` and every entry of ``opt.compute_gradients(mse_, theta_)`` agree
+to 1e-9 (goldens tests/golden/picnn_tfshim.npz); (ii) an independently written torch autograd
+(float64, ``create_graph=True``) of the same recurrence; (iii) central finite differences.  Not executable here:
+the real TensorFlow kernels (the stand-in's autodiff is torch's).
 
 Derivation (ReLU / leaky-ReLU energies are piecewise linear in y, so d2f/dy2 = 0 almost everywhere,
 exactly what TF's ReluGrad-of-ReluGrad yields):

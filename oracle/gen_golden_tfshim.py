@@ -1,0 +1,245 @@
+#!/usr/bin/env python
+"""Golden vectors for the PICNN energy f, df/dy, the unrolled momentum-GD loop and its training gradient,
+produced by EXECUTING THE REFERENCE'S OWN graph code (cut out of its files with ``ast``, unmodified) on
+oracle/tf_shim.py -- TensorFlow / tflearn are not installed, the shim restates only their primitives.
+
+Executed reference code (paths under /root/reference):
+  multi-label-cls/icnn_ebundle.py  class Model: __init__ (:120-166) and f (:316-388)  -> E_, dE_dy_
+  multi-label-cls/icnn-back.py     class Model: __init__ (:104-147) and f (:233-305)  -> yn_, energies_, mse_,
+                                   opt.compute_gradients(mse_, theta_)
+  RL/src/icnn.py                   class Agent: negQ (:325-404), bundle_entropy (:148-158)
+  RL/src/bundle_entropy.py         solveBatch (imported unchanged, called BY Agent.bundle_entropy)
+
+The goldens pin oracle/picnn_np.py (f, df/dy, gates incl. batch-norm, momentum GD, the RL affine wrapper) and
+oracle/gd_grad_np.py (training gradient through the unrolled loop) -- tests/test_oracle_tfshim.py -- and are
+compared with the device kernels in tests/test_gpu_picnn.py.  Weights and inputs are regenerated from seeds by
+``case_inputs`` (shared with the tests); only outputs are stored.
+
+TEST INFRASTRUCTURE ONLY; runs in the build container only (needs /root/reference).
+Usage:  python oracle/gen_golden_tfshim.py
+"""
+import ast
+import contextlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from icnn_b200 import workloads  # noqa: E402  (pure-numpy input generator)
+
+REF = "/root/reference"
+BN_EPS = 1e-5
+
+
+# --------------------------------------------------------------------------------------------------------
+# seeded inputs (shared with the tests)
+# --------------------------------------------------------------------------------------------------------
+
+def _f32(a):
+    return np.asarray(a, dtype=np.float32).astype(np.float64)
+
+
+def _random_biases(p, rs):
+    """Non-zero biases everywhere the reference has one, so that bias placement is pinned too."""
+    for i in range(p.L):
+        p.bu[i] = _f32(0.3 * rs.randn(p.hidden[i]))
+    for i in range(p.L + 1):
+        if i > 0:
+            p.bzu[i] = _f32(0.3 * rs.randn(p.sizes[i - 1]))
+        p.byu[i] = _f32(0.5 + 0.3 * rs.randn(p.n))
+        p.bzx[i] = _f32(0.3 * rs.randn(p.sizes[i]))
+
+
+def case_inputs(tag):
+    """-> dict(p, x, y, bnvars, and the case's scalars).  ``bnvars[i]`` = (gamma, beta, moving_mean, moving_variance)
+    of the batch-norm after u_i (multi-label f applies one for every i < L-1), ``p.bn`` the matching affine map or
+    None when the variables are the identity (variance 1 - eps, so that variance + eps = 1)."""
+    rs = np.random.RandomState(abs(hash_tag(tag)) % (2 ** 31))
+    c = dict(tag=tag)
+    if tag == "ml_fg_c3":            # the shape / inputs of tests/test_gpu_picnn.py::test_fg_matches_oracle[C3-77]
+        p, x, y0 = workloads.make_inputs("C3", B=77)
+        y = _f32(np.random.RandomState(11).uniform(0.02, 0.98, size=y0.shape))
+        c.update(p=p, x=x, y=y, layerSizes=[600])
+    elif tag == "ml_fg_bn":          # three z-layers, odd widths, biases, real batch-norm statistics
+        p = workloads.synth_params(31, 10, 7, [12, 9, 7])
+        _random_biases(p, rs)
+        x = _f32(rs.randn(16, 10))
+        y = _f32(rs.uniform(0.02, 0.98, size=(16, 7)))
+        c.update(p=p, x=x, y=y, layerSizes=[12, 9])
+        c["bnvars"] = [(_f32(rs.uniform(0.5, 1.5, s)), _f32(0.2 * rs.randn(s)), _f32(0.3 * rs.randn(s)),
+                        _f32(rs.uniform(0.5, 2.0, s))) for s in p.hidden[:-1]]
+    elif tag == "rl_fg_c4":          # the shape / inputs of test_fg_matches_oracle[C4-300]
+        p, x, y0 = workloads.make_inputs("C4", B=300)
+        y = _f32(np.random.RandomState(11).uniform(0.02, 0.98, size=y0.shape))
+        c.update(p=p, x=x, y=y)
+    elif tag == "rl_act_c4":         # Agent.bundle_entropy end to end (reference solveBatch on the reference negQ)
+        p, x, y0 = workloads.make_inputs("C4", B=48)
+        c.update(p=p, x=x, y=y0)
+    elif tag == "gd_c3":             # the case of test_momentum_gd_matches_oracle[C3-50-0.01-0.3] (script defaults)
+        p, x, y0 = workloads.make_inputs("C3", B=50)
+        c.update(p=p, x=x, y=y0, layerSizes=[600], lr=0.01, momentum=0.3, nIter=30,
+                 trueY=(rs.uniform(size=y0.shape) < 0.1).astype(np.float64))
+    elif tag == "gdgrad_small":      # every parameter gradient of the unrolled loop on a net small enough to store
+        p = workloads.synth_params(32, 12, 9, [14, 11, 9])
+        for i in range(len(p.Wy)):
+            p.Wy[i] = _f32(3.0 * p.Wy[i])
+        _random_biases(p, rs)
+        x = _f32(rs.randn(20, 12))
+        c.update(p=p, x=x, y=np.full((20, 9), 0.5), layerSizes=[14, 11], lr=0.02, momentum=0.5, nIter=7,
+                 trueY=(rs.uniform(size=(20, 9)) < 0.3).astype(np.float64))
+    else:
+        raise KeyError(tag)
+    p = c["p"]
+    if "bnvars" in c:
+        p.bn = [workloads.bn_affine(*v, eps=BN_EPS) for v in c["bnvars"]] + [None]
+    elif p.alpha == 0.0:             # multi-label f always applies bn: identity statistics
+        c["bnvars"] = [(np.ones(s), np.zeros(s), np.zeros(s), np.full(s, 1.0 - BN_EPS)) for s in p.hidden[:-1]]
+    return c
+
+
+def hash_tag(tag):
+    return sum((i + 1) * ord(ch) for i, ch in enumerate(tag)) * 7919
+
+
+CASES = ["ml_fg_c3", "ml_fg_bn", "rl_fg_c4", "rl_act_c4", "gd_c3", "gdgrad_small"]
+
+
+# --------------------------------------------------------------------------------------------------------
+# reference code on the shim
+# --------------------------------------------------------------------------------------------------------
+
+def variables_from_params(p, bnvars=None, prefix=""):
+    """PicnnParams -> {tensorflow variable name: array}, the naming of the reference's variable scopes
+    (multi-label-cls/icnn_ebundle.py:341,353,356,363,366,372; RL/src/icnn.py:346,361,366,373,377,384)."""
+    v = {}
+    for i in range(p.L):
+        v["%su%d/W" % (prefix, i)] = p.Wu[i]
+        v["%su%d/b" % (prefix, i)] = p.bu[i]
+        if bnvars is not None and i < p.L - 1:
+            for nm, a in zip(("gamma", "beta", "moving_mean", "moving_variance"), bnvars[i]):
+                v["%su%d/bn/%s" % (prefix, i, nm)] = a
+    for i in range(p.L + 1):
+        if i > 0:
+            v["%sz%d_zu_u/W" % (prefix, i)] = p.Wzu[i]
+            v["%sz%d_zu_u/b" % (prefix, i)] = p.bzu[i]
+            v["%sz%d_zu_proj/W" % (prefix, i)] = p.Wz[i]
+        v["%sz%d_yu_u/W" % (prefix, i)] = p.Wyu[i]
+        v["%sz%d_yu_u/b" % (prefix, i)] = p.byu[i]
+        v["%sz%d_yu/W" % (prefix, i)] = p.Wy[i]
+        v["%sz%d_u/W" % (prefix, i)] = p.Wzx[i]
+        v["%sz%d_u/b" % (prefix, i)] = p.bzx[i]
+    return v
+
+
+def extract(path, names, namespace):
+    """exec the top-level class / function definitions ``names`` of a reference file, verbatim, in ``namespace``."""
+    tree = ast.parse(open(path).read())
+    body = [n for n in tree.body if isinstance(n, (ast.ClassDef, ast.FunctionDef)) and n.name in names]
+    assert len(body) == len(names), (path, names)
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), namespace)
+    return namespace
+
+
+def _shim(c, feeds, prefix=""):
+    from oracle.tf_shim import Shim
+    sh = Shim(variables_from_params(c["p"], c.get("bnvars"), prefix))
+    sh.tf.trainable_variables = lambda: [sh.vars[k] for k in sh.created if "moving_" not in k]   # creation order, as TF
+    for k, (a, rg) in feeds.items():
+        sh.feed(k, a, requires_grad=rg)
+    return sh
+
+
+def run_multilabel_model(c, path, ctor_args):
+    """Model(...) of a multi-label script: building it evaluates the whole graph on the fed tensors."""
+    B, n = c["y"].shape
+    rs = np.random.RandomState(5)
+    feeds = {"x": (c["x"], False), "y": (c["y"], True), "trueY": (c.get("trueY", np.zeros((B, n))), False),
+             "v": (rs.randn(B, n), False), "c": (rs.randn(B), False)}
+    sh = _shim(c, feeds)
+    ns = extract(path, ["Model"], {"tf": sh.tf, "tflearn": sh.tflearn, "np": np,
+                                   "variable_summaries": lambda *a, **k: None})
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = ns["Model"](c["p"].m, c["p"].n, *ctor_args, None)
+    assert not sh.unused_variables(), sh.unused_variables()
+    assert model.szs == c["p"].hidden
+    return sh, model
+
+
+def run_negq(c, agent_ns, obs, act):
+    """One evaluation of Agent.negQ and tf.gradients(negQ, act) (RL/src/icnn.py:59-63), under scope 'q'."""
+    sh = _shim(c, {"obs": (obs, False), "act": (act, True)}, prefix="q/")
+    agent_ns["tf"], agent_ns["tflearn"] = sh.tf, sh.tflearn
+    agent = agent_ns["Agent"].__new__(agent_ns["Agent"])
+    agent.dimA, agent.dimO = c["p"].n, c["p"].m
+    agent.sess = types.SimpleNamespace(close=lambda: None)
+    with sh.tf.variable_scope("q"):
+        negQ = agent.negQ(sh.feeds["obs"], sh.feeds["act"])
+    (grad,) = sh.tf.gradients(negQ, sh.feeds["act"])
+    assert not sh.unused_variables(), sh.unused_variables()
+    return agent, negQ.detach().numpy().copy(), grad.detach().numpy().copy()
+
+
+def main():
+    sys.path.insert(0, os.path.join(REF, "RL", "src"))
+    from oracle.gen_golden import _load
+    out = {}
+
+    # ---- multi-label Model (bundle-entropy script): E_ and dE_dy_ ------------------------------------------------
+    for tag in ("ml_fg_c3", "ml_fg_bn"):
+        c = case_inputs(tag)
+        sh, model = run_multilabel_model(c, os.path.join(REF, "multi-label-cls/icnn_ebundle.py"), (list(c["layerSizes"]),))
+        out[tag + "_f"] = model.E_.detach().numpy()
+        out[tag + "_g"] = model.dE_dy_.detach().numpy()
+        out[tag + "_g_entr"] = model.dE_entr_dy_.detach().numpy()
+        print(tag, "variables in creation order:", len(sh.created), "f[:3]", out[tag + "_f"][:3])
+
+    # ---- RL Agent.negQ and Agent.bundle_entropy ---------------------------------------------------------------
+    flags = types.SimpleNamespace(l1size=200, l2size=200, icnn_bn=False, lrelu=0.01)
+    ref_rl = _load("bundle_entropy", os.path.join(REF, "RL/src/bundle_entropy.py"))
+    agent_ns = {"np": np, "FLAGS": flags, "bundle_entropy": ref_rl, "variable_summaries": lambda *a, **k: None}
+    extract(os.path.join(REF, "RL/src/icnn.py"), ["Agent"], agent_ns)
+    c = case_inputs("rl_fg_c4")
+    # the wrapper of Agent.bundle_entropy (:150-153), applied by hand for the fg golden: a = 2x - 1, grad *= 2
+    _agent, f, g = run_negq(c, agent_ns, c["x"], 2.0 * c["y"] - 1.0)
+    out["rl_fg_c4_f"], out["rl_fg_c4_g"] = f, 2.0 * g
+    c = case_inputs("rl_act_c4")
+    agent, _f, _g = run_negq(c, agent_ns, c["x"], 2.0 * c["y"] - 1.0)
+
+    def func(obs, act):                      # what Fun([obs, act], [negQ, act_grad]) returns (:107)
+        _a, f_, g_ = run_negq(c, agent_ns, obs, act)
+        return f_, g_
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+        out["rl_act_c4_act"] = agent.bundle_entropy(func, c["x"])
+    print("rl_act_c4 act[0]", out["rl_act_c4_act"][0])
+
+    # ---- multi-label Model (back-optimisation script): unrolled momentum GD and its training gradient ----------
+    for tag in ("gd_c3", "gdgrad_small"):
+        c = case_inputs(tag)
+        args = types.SimpleNamespace(layerSizes=list(c["layerSizes"]), inference_lr=c["lr"],
+                                     inference_momentum=c["momentum"], inference_nIter=c["nIter"])
+        sh, model = run_multilabel_model(c, os.path.join(REF, "multi-label-cls/icnn-back.py"), (args,))
+        out[tag + "_yN"] = model.yn_.detach().numpy()
+        out[tag + "_energies"] = model.energies_.detach().numpy()
+        out[tag + "_mse"] = np.array(float(model.mse_.detach()))
+        names = []
+        for g_, v_ in sh.tf.train.AdamOptimizer().compute_gradients(model.mse_, model.theta_):
+            nm = v_.name[:-2].replace("/", "__")
+            names.append(nm)
+            ga = np.zeros(tuple(v_.value.shape)) if g_ is None else g_.detach().numpy()
+            if tag == "gdgrad_small" or ga.size <= 1024:      # gd_c3: biases and the width-1 output layer only
+                out["%s_grad_%s" % (tag, nm)] = ga
+        out[tag + "_theta"] = np.array(names)
+        print(tag, "mse", out[tag + "_mse"], "theta", len(names), "stored grads",
+              sum(k.startswith(tag + "_grad_") for k in out))
+
+    path = os.path.join(ROOT, "tests", "golden", "picnn_tfshim.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, len(out), "arrays,", os.path.getsize(path) // 1024, "KB")
+
+
+if __name__ == "__main__":
+    main()

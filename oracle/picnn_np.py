@@ -1,8 +1,8 @@
 """numpy float64 restatement of the fully-connected PICNN energy f(x, y; theta) and df/dy.
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  The reference builds this function as a
-TensorFlow graph, which cannot run here (TensorFlow/tflearn absent), so it is restated from the
-cited lines; tflearn ``fully_connected`` is ``out = in @ W + b`` with W laid out ``[in, out]``.
+TensorFlow graph (TensorFlow/tflearn absent here), so it is restated from the cited lines; tflearn
+``fully_connected`` is ``out = in @ W + b`` with W laid out ``[in, out]``.
 
 Follows (paths relative to /root/reference):
   * multi-label-cls/icnn_ebundle.py:316-388  (Model.f: ReLU PICNN, ``nLabels`` appended to szs)
@@ -11,9 +11,14 @@ Follows (paths relative to /root/reference):
   * RL/src/icnn.py:148-158                   (affine wrapper x in [0,1] -> a = 2x-1, grad *= 2)
   * multi-label-cls/icnn-back.py:116-131     (momentum gradient-descent inner loop)
 
-Parity status of THIS file: "parity unpinned" by reference execution (the TF graph cannot be
-run); it is pinned instead by (i) a finite-difference check of the analytic gradient and
-(ii) an independently written torch-autograd forward (tests/test_oracle_picnn.py).
+Parity status of THIS file: TensorFlow / tflearn are not installed, so the reference's graph cannot run on
+the real libraries.  It is pinned three ways (tests/test_oracle_picnn.py, tests/test_oracle_tfshim.py):
+(i) **the reference's own code** -- Model.__init__/f of both multi-label scripts and Agent.negQ /
+Agent.bundle_entropy, cut out of the reference files unmodified -- executed on a stand-in that restates only the
+TF / tflearn PRIMITIVES (oracle/tf_shim.py; goldens tests/golden/picnn_tfshim.npz by oracle/gen_golden_tfshim.py):
+f, df/dy, gates with batch-norm, momentum GD and the RL wrapper agree to 1e-10; (ii) a finite-difference check of
+the analytic gradient; (iii) an independently written torch-autograd forward.  What stays restated rather than
+executed is the primitives' semantics (``fully_connected`` = ``x @ W + b``, batch-norm epsilon 1e-5, leaky-ReLU).
 
 Index convention: z-layers i = 0..L, widths s_0..s_{L-1} = ``hidden``, s_L = 1.
 """

@@ -36,6 +36,38 @@ def test_fg_matches_oracle(name, B):
     assert np.abs(g - go).max() <= tol * max(1.0, np.abs(go).max())
 
 
+@pytest.mark.parametrize("tag,affine", [("ml_fg_c3", False), ("rl_fg_c4", True)])
+def test_fg_matches_the_reference_graph_golden(tag, affine, golden_dir):
+    """K1 against tests/golden/picnn_tfshim.npz: E_ / dE_dy_ of the reference's OWN Model.f
+    (multi-label-cls/icnn_ebundle.py:316-388,146) and Agent.negQ under the bundle_entropy wrapper
+    (RL/src/icnn.py:325-404,150-153), executed unmodified on oracle/tf_shim.py (oracle/gen_golden_tfshim.py).
+    Same inputs and tolerance as test_fg_matches_oracle[C3-77] / [C4-300]."""
+    import os
+    import icnn_b200
+    from oracle.gen_golden_tfshim import case_inputs
+    gold = np.load(os.path.join(golden_dir, "picnn_tfshim.npz"))
+    c = case_inputs(tag)
+    f, g = icnn_b200.PICNN.from_params(c["p"]).bind(c["x"], affine=affine)(c["y"])
+    fo, go = gold[tag + "_f"], gold[tag + "_g"]
+    assert np.abs(f - fo).max() <= 1e-5 * max(1.0, np.abs(fo).max())
+    assert np.abs(g - go).max() <= 1e-5 * max(1.0, np.abs(go).max())
+
+
+def test_momentum_gd_matches_the_reference_graph_golden(golden_dir):
+    """yn_ / energies_ of the reference's unrolled graph (multi-label-cls/icnn-back.py:116-131, script defaults
+    lr .01, momentum .3, 30 steps; C3 dims, 50 rows), golden from the reference code on oracle/tf_shim.py."""
+    import os
+    import icnn_b200
+    from oracle.gen_golden_tfshim import case_inputs
+    gold = np.load(os.path.join(golden_dir, "picnn_tfshim.npz"))
+    c = case_inputs("gd_c3")
+    fg = icnn_b200.PICNN.from_params(c["p"]).bind(c["x"])
+    y, f = icnn_b200.gd.solve(fg, c["y"], nIter=c["nIter"], lr=c["lr"], momentum=c["momentum"])
+    yo, fo = gold["gd_c3_yN"], gold["gd_c3_energies"]
+    assert np.abs(y - yo).max() < 2e-5
+    assert np.abs(f - fo).max() <= 2e-5 * max(1.0, np.abs(fo).max())
+
+
 def test_long_reductions_carry_no_systematic_bias():
     """C5 dims (K up to 5120 per GEMM, four hidden layers): the tensor core truncates its FP32 accumulator at
     every MMA; uncorrected that is a systematic -2e-5 relative scaling of f and g which moves y* by 3e-3 at the
