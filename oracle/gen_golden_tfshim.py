@@ -7,7 +7,7 @@ Executed reference code (paths under /root/reference):
   multi-label-cls/icnn_ebundle.py  class Model: __init__ (:120-166) and f (:316-388)  -> E_, dE_dy_
   multi-label-cls/icnn-back.py     class Model: __init__ (:104-147) and f (:233-305)  -> yn_, energies_, mse_,
                                    opt.compute_gradients(mse_, theta_)
-  RL/src/icnn.py                   class Agent: negQ (:325-404), bundle_entropy (:148-158)
+  RL/src/icnn.py                   class Agent: negQ (:325-404), bundle_entropy (:148-158); entropy (:455-458)
   RL/src/bundle_entropy.py         solveBatch (imported unchanged, called BY Agent.bundle_entropy)
 
 The goldens pin oracle/picnn_np.py (f, df/dy, gates incl. batch-norm, momentum GD, the RL affine wrapper) and
@@ -76,6 +76,11 @@ def case_inputs(tag):
         p, x, y0 = workloads.make_inputs("C4", B=300)
         y = _f32(np.random.RandomState(11).uniform(0.02, 0.98, size=y0.shape))
         c.update(p=p, x=x, y=y)
+    elif tag == "rl_fg_entr_c4":     # func = _fg_entr of Agent.adam: actions in [-1, 1] incl. the clipped ends of entropy()
+        p, x, y0 = workloads.make_inputs("C4", B=40)
+        a = _f32(rs.uniform(-1.0, 1.0, size=y0.shape))
+        a[::7, 0], a[3::9, 2] = 1.0 - 1e-8, -1.0 + 1e-8      # where Agent.adam clips to (:211)
+        c.update(p=p, x=x, y=a)
     elif tag == "rl_act_c4":         # Agent.bundle_entropy end to end (reference solveBatch on the reference negQ)
         p, x, y0 = workloads.make_inputs("C4", B=48)
         c.update(p=p, x=x, y=y0)
@@ -105,7 +110,7 @@ def hash_tag(tag):
     return sum((i + 1) * ord(ch) for i, ch in enumerate(tag)) * 7919
 
 
-CASES = ["ml_fg_c3", "ml_fg_bn", "rl_fg_c4", "rl_act_c4", "gd_c3", "gdgrad_small"]
+CASES = ["ml_fg_c3", "ml_fg_bn", "rl_fg_c4", "rl_fg_entr_c4", "rl_act_c4", "gd_c3", "gdgrad_small"]
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -169,7 +174,7 @@ def run_multilabel_model(c, path, ctor_args):
     return sh, model
 
 
-def run_negq(c, agent_ns, obs, act):
+def run_negq(c, agent_ns, obs, act, entr=False):
     """One evaluation of Agent.negQ and tf.gradients(negQ, act) (RL/src/icnn.py:59-63), under scope 'q'."""
     sh = _shim(c, {"obs": (obs, False), "act": (act, True)}, prefix="q/")
     agent_ns["tf"], agent_ns["tflearn"] = sh.tf, sh.tflearn
@@ -180,6 +185,10 @@ def run_negq(c, agent_ns, obs, act):
         negQ = agent.negQ(sh.feeds["obs"], sh.feeds["act"])
     (grad,) = sh.tf.gradients(negQ, sh.feeds["act"])
     assert not sh.unused_variables(), sh.unused_variables()
+    if entr:        # negQ_entr = negQ - entropy(act), act_grad_entr (RL/src/icnn.py:60-63, entropy :455-458)
+        negQ_entr = negQ - agent_ns["entropy"](sh.feeds["act"])
+        (grad_entr,) = sh.tf.gradients(negQ_entr, sh.feeds["act"])
+        return agent, negQ_entr.detach().numpy().copy(), grad_entr.detach().numpy().copy()
     return agent, negQ.detach().numpy().copy(), grad.detach().numpy().copy()
 
 
@@ -201,11 +210,13 @@ def main():
     flags = types.SimpleNamespace(l1size=200, l2size=200, icnn_bn=False, lrelu=0.01)
     ref_rl = _load("bundle_entropy", os.path.join(REF, "RL/src/bundle_entropy.py"))
     agent_ns = {"np": np, "FLAGS": flags, "bundle_entropy": ref_rl, "variable_summaries": lambda *a, **k: None}
-    extract(os.path.join(REF, "RL/src/icnn.py"), ["Agent"], agent_ns)
+    extract(os.path.join(REF, "RL/src/icnn.py"), ["Agent", "entropy"], agent_ns)
     c = case_inputs("rl_fg_c4")
     # the wrapper of Agent.bundle_entropy (:150-153), applied by hand for the fg golden: a = 2x - 1, grad *= 2
     _agent, f, g = run_negq(c, agent_ns, c["x"], 2.0 * c["y"] - 1.0)
     out["rl_fg_c4_f"], out["rl_fg_c4_g"] = f, 2.0 * g
+    c = case_inputs("rl_fg_entr_c4")
+    _agent, out["rl_fg_entr_c4_f"], out["rl_fg_entr_c4_g"] = run_negq(c, agent_ns, c["x"], c["y"], entr=True)
     c = case_inputs("rl_act_c4")
     agent, _f, _g = run_negq(c, agent_ns, c["x"], 2.0 * c["y"] - 1.0)
 

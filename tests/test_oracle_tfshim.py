@@ -56,6 +56,17 @@ def test_rl_negq_and_affine_wrapper_match_the_reference_graph(gold):
     close(g, gold["rl_fg_c4_g"], "grad")
 
 
+def test_rl_entropy_regularised_objective_matches_the_reference_graph(gold):
+    """func = _fg_entr of the RL agent's Adam argmin: negQ - entropy(act) and its action gradient
+    (RL/src/icnn.py:60-63, entropy :455-458 -- tf.clip_by_value passes no gradient outside [1e-4, 1 - 1e-4]),
+    including actions at the ends Agent.adam clips to (:211)."""
+    from oracle import adam_np
+    c = case_inputs("rl_fg_entr_c4")
+    f, g = adam_np.make_fg_entr(c["p"], c["x"])(c["x"], c["y"])
+    close(f, gold["rl_fg_entr_c4_f"], "negQ_entr")
+    close(g, gold["rl_fg_entr_c4_g"], "act_grad_entr")
+
+
 def test_rl_action_selection_end_to_end(gold, golden_dir):
     """Agent.bundle_entropy(func, obs) executed in full by the generator -- the reference's negQ graph inside the
     reference's RL solveBatch -- against the oracle pair (picnn_np + bundle_np), and against the solver golden
