@@ -6,8 +6,8 @@ and assembles the per-bundle-point (v, c) pairs the training step feeds back to 
     mseGrad         completion/icnn_ebundle.py:493-522
     train_step_fd   multi-label-cls/icnn_ebundle.py:296-314 / completion/icnn_ebundle.py:315-335
 Pinned by tests/golden/argmin_grad.npz, produced by exec'ing the reference's own function
-bodies (extracted with ast; the scripts themselves import TensorFlow at module level and cannot
-be imported) -- oracle/gen_golden_grad.py.
+bodies and the reference's own ``Model.train_step_fd`` methods (extracted with ast; the scripts
+themselves import TensorFlow at module level and cannot be imported) -- oracle/gen_golden_grad.py.
 """
 import numpy as np
 

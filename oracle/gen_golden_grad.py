@@ -32,6 +32,26 @@ def extract(path, name):
     raise KeyError(name)
 
 
+def extract_class(path, cls, namespace):
+    """exec a top-level class of a reference file verbatim (its methods may use the module-level functions
+    already present in ``namespace``)."""
+    tree = ast.parse(open(path).read())
+    node = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls]
+    exec(compile(ast.Module(body=node, type_ignores=[]), path, "exec"), namespace)
+    return namespace[cls]
+
+
+def train_step_fd_golden(path, gradfn_name, gradfn, B, xBatch, trueY, G, yN, ys, lam, output_shape=None):
+    """The reference's own Model.train_step_fd (multi-label-cls/icnn_ebundle.py:296-314,
+    completion/icnn_ebundle.py:315-335) on a stub ``self`` (placeholders = dictionary keys)."""
+    import types
+    Model = extract_class(path, "Model", {"np": np, gradfn_name: gradfn})
+    stub = types.SimpleNamespace(x_="x", y_="y", v_="v", c_="c", outputSz=output_shape)
+    with np.errstate(all="ignore"):
+        fd = Model.train_step_fd(stub, B, xBatch, trueY, G, yN, ys, lam)
+    return fd
+
+
 def main():
     xent = extract(os.path.join(REF, "multi-label-cls/icnn_ebundle.py"), "crossEntrGrad")
     mse = extract(os.path.join(REF, "completion/icnn_ebundle.py"), "mseGrad")
@@ -55,6 +75,15 @@ def main():
             out["%s_%s_cy" % (tag, name)] = cy
             out["%s_%s_clam" % (tag, name)] = clam
             out["%s_%s_ct" % (tag, name)] = ct
+        # the (v, c) assembly of the training step, by the reference's own method
+        for name, fn, path, gname, oshape in (
+                ("xent", xent, "multi-label-cls/icnn_ebundle.py", "crossEntrGrad", None),
+                ("mse", mse, "completion/icnn_ebundle.py", "mseGrad", (yN.shape[1],))):
+            fd = train_step_fd_golden(os.path.join(REF, path), gname, fn, B, x, trueY, G, yN, ys, lam, oshape)
+            assert np.array_equal(fd["x"], np.repeat(x, [len(g) for g in G], axis=0))
+            out["%s_%s_fd_ys" % (tag, name)] = fd["y"]
+            out["%s_%s_fd_vs" % (tag, name)] = fd["v"]
+            out["%s_%s_fd_cs" % (tag, name)] = fd["c"]
         out[tag + "_trueY"] = trueY
         out[tag + "_yN"] = yN
         out[tag + "_counts"] = np.array([len(g) for g in G])

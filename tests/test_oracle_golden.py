@@ -99,6 +99,27 @@ def test_argmin_grad_restatement_matches_reference_bodies(golden_dir):
                                            atol=1e-7 * max(1.0, np.abs(clam).max()))
 
 
+def test_train_step_pairs_match_the_reference_method(golden_dir):
+    """oracle/argmin_grad_np.train_step_pairs vs the (fd_ys, fd_vs, fd_cs) feeds built by the reference's own
+    Model.train_step_fd (multi-label-cls/icnn_ebundle.py:296-314 with crossEntrGrad,
+    completion/icnn_ebundle.py:315-335 with mseGrad), exec'd unmodified by oracle/gen_golden_grad.py."""
+    from oracle import argmin_grad_np
+    gold = np.load(os.path.join(golden_dir, "argmin_grad.npz"))
+    for tag, cfgname, B, nIter in (("c1", "C1", 32, 5), ("c3", "C3", 12, 10)):
+        p, x, y0 = synth.make_inputs(cfgname, B=B)
+        with np.errstate(all="ignore"):
+            yN, G, h, lam, ys, _ = bundle_np.solve_batch(picnn_np.make_fg(p, x), y0.copy(), nIter=nIter)
+        for loss in ("xent", "mse"):
+            with np.errstate(all="ignore"):
+                fys, fvs, fcs = argmin_grad_np.train_step_pairs(yN, gold[tag + "_trueY"], G, ys, lam, loss)
+            rys, rvs, rcs = (gold["%s_%s_fd_%s" % (tag, loss, k)] for k in ("ys", "vs", "cs"))
+            assert fys.shape == rys.shape and fvs.shape == rvs.shape and fcs.shape == rcs.shape
+            np.testing.assert_allclose(fys, rys, rtol=0, atol=1e-9)
+            scale = max(1.0, np.abs(rvs).max(), np.abs(rcs).max())
+            np.testing.assert_allclose(fvs, rvs, rtol=0, atol=1e-7 * scale)
+            np.testing.assert_allclose(fcs, rcs, rtol=0, atol=1e-7 * scale)
+
+
 def test_adam_restatement_matches_reference_body(golden_dir):
     """oracle/adam_np.py vs Agent.adam exec'd from RL/src/icnn.py (oracle/gen_golden_adam.py)."""
     from oracle import adam_np
