@@ -9,6 +9,9 @@ Executed reference code (paths under /root/reference):
                                    opt.compute_gradients(mse_, theta_)
   RL/src/icnn.py                   class Agent: negQ (:325-404), bundle_entropy (:148-158); entropy (:455-458)
   RL/src/bundle_entropy.py         solveBatch (imported unchanged, called BY Agent.bundle_entropy)
+  completion/icnn_ebundle.py       class Model: __init__ (:105-161) and f (:337-452): the CONVOLUTIONAL PICNN of the
+                                   Olivetti experiment -> E_, dE_dy_; pins tests/conv_picnn.py, the user-side ``fg`` the
+                                   GPU callback-mode test drives K2 with
 
 The goldens pin oracle/picnn_np.py (f, df/dy, gates incl. batch-norm, momentum GD, the RL affine wrapper) and
 oracle/gd_grad_np.py (training gradient through the unrolled loop) -- tests/test_oracle_tfshim.py -- and are
@@ -192,6 +195,85 @@ def run_negq(c, agent_ns, obs, act, entr=False):
     return agent, negQ.detach().numpy().copy(), grad.detach().numpy().copy()
 
 
+# ---- the convolutional PICNN of completion/ (callback-mode fg of the GPU tests) ---------------------------------
+
+CONV_CASES = {"conv_small": (4, 16, 8, 3), "conv_olivetti": (2, 64, 32, 1)}     # tag -> (B, H, W, seed)
+
+
+def conv_case(tag):
+    """-> (ConvPICNN float64, x [B, H*W], y [B, H*W]) of tests/conv_picnn.py, seeded."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conv_picnn import ConvPICNN
+    B, H, W, seed = CONV_CASES[tag]
+    net = ConvPICNN(H, W, seed=seed, dtype=torch.float64)
+    rs = np.random.RandomState(100 + seed)
+    return net, rs.uniform(size=(B, H * W)), rs.uniform(0.05, 0.95, size=(B, H * W))
+
+
+def conv_variables(net):
+    """tests/conv_picnn.py parameters -> the reference's variable names and TensorFlow layouts: conv kernels
+    [k, k, c_in, c_out]; the dense layers behind the last conv see its feature map flattened in NHWC order."""
+    from conv_picnn import CONVS, FCS
+    P = net.P
+    v = {}
+    nc = len(CONVS)
+    cw = lambda w: w.permute(2, 3, 1, 0).numpy()                                    # noqa: E731
+    h, w = net.H, net.W
+    for (_nf, _k, s_) in CONVS:
+        h, w = -(-h // s_), -(-w // s_)
+    C = CONVS[-1][0]
+    perm = np.arange(C * h * w).reshape(C, h, w).transpose(1, 2, 0).reshape(-1)     # NHWC position -> NCHW index
+    for i in range(nc + len(FCS)):
+        conv = i < nc
+        Wu, bu = P["u%d" % i]
+        v["u%d/W" % i] = cw(Wu) if conv else (Wu.numpy()[perm] if i == nc else Wu.numpy())
+        v["u%d/b" % i] = bu.numpy()
+        width = Wu.shape[0] if conv else Wu.shape[1]
+        if conv or width != 1:          # bn(...) on every u layer but the width-1 one (:352-366); identity statistics
+            for nm, a in (("gamma", np.ones(width)), ("beta", np.zeros(width)), ("moving_mean", np.zeros(width)),
+                          ("moving_variance", np.full(width, 1.0 - BN_EPS))):
+                v["u%d/BatchNormalization/%s" % (i, nm)] = a
+        if i > 0:
+            Wq, bq = P["zu_u%d" % i]
+            if conv:
+                v["z%d_zu_u/W" % i], v["z%d_zu_proj/W" % i] = cw(Wq), cw(P["zu_proj%d" % i])
+                v["z%d_zu_u/b" % i] = bq.numpy()
+            elif i == nc:
+                v["z%d_zu_u/W" % i], v["z%d_zu_u/b" % i] = Wq.numpy()[perm][:, perm], bq.numpy()[perm]
+                v["z%d_zu_proj/W" % i] = P["zu_proj%d" % i].numpy()[perm]
+            else:
+                v["z%d_zu_u/W" % i], v["z%d_zu_u/b" % i] = Wq.numpy(), bq.numpy()
+                v["z%d_zu_proj/W" % i] = P["zu_proj%d" % i].numpy()
+        if conv:
+            v["z%d_yu_u/W" % i], v["z%d_yu_u/b" % i] = cw(P["yu_u%d" % i][0]), P["yu_u%d" % i][1].numpy()
+            v["z%d_yu/W" % i] = cw(P["yu%d" % i])
+            v["z%d_y_red/W" % i], v["z%d_y_red/b" % i] = cw(P["y_red%d" % i][0]), P["y_red%d" % i][1].numpy()
+        Wz, bz = P["z_u%d" % i]
+        v["z%d_u/W" % i] = cw(Wz) if conv else (Wz.numpy()[perm] if i == nc else Wz.numpy())
+        v["z%d_u/b" % i] = bz.numpy()
+    return v
+
+
+def run_completion_model(tag):
+    from oracle.tf_shim import Shim
+    net, x, y = conv_case(tag)
+    B, H, W, _ = CONV_CASES[tag]
+    sh = Shim(conv_variables(net))
+    sh.tf.trainable_variables = lambda: [sh.vars[k] for k in sh.created if "moving_" not in k]
+    rs = np.random.RandomState(5)
+    for k, a, rg in (("x", x.reshape(B, H, W, 1), False), ("y", y.reshape(B, H, W, 1), True),
+                     ("trueY", np.zeros((B, H, W, 1)), False), ("v", rs.randn(B, H * W), False), ("c", rs.randn(B), False),
+                     ("l_yN", np.zeros(()), False), ("nBundleIter", np.zeros(B), False), ("nActive", np.zeros(B), False)):
+        sh.feed(k, a, requires_grad=rg)
+    ns = extract(os.path.join(REF, "completion/icnn_ebundle.py"), ["Model"],
+                 {"tf": sh.tf, "tflearn": sh.tflearn, "np": np, "variable_summaries": lambda *a, **k: None})
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = ns["Model"]([H, W, 1], [H, W, 1], None)
+    assert not sh.unused_variables(), sh.unused_variables()
+    return model.E_.detach().numpy(), model.dE_dyFlat_.detach().numpy(), len(sh.created)
+
+
 def main():
     sys.path.insert(0, os.path.join(REF, "RL", "src"))
     from oracle.gen_golden import _load
@@ -246,6 +328,11 @@ def main():
         out[tag + "_theta"] = np.array(names)
         print(tag, "mse", out[tag + "_mse"], "theta", len(names), "stored grads",
               sum(k.startswith(tag + "_grad_") for k in out))
+
+    # ---- completion Model: the convolutional PICNN ------------------------------------------------------------------
+    for tag in CONV_CASES:
+        out[tag + "_f"], out[tag + "_g"], nv = run_completion_model(tag)
+        print(tag, "variables", nv, "f", out[tag + "_f"])
 
     path = os.path.join(ROOT, "tests", "golden", "picnn_tfshim.npz")
     np.savez_compressed(path, **out)

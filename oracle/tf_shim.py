@@ -8,6 +8,7 @@ network):
   * multi-label-cls/icnn-back.py:104-147,233-305     Model.__init__ / Model.f        (unrolled momentum GD, mse_,
                                                                                       opt.compute_gradients)
   * RL/src/icnn.py:325-404, 148-158                  Agent.negQ / Agent.bundle_entropy
+  * completion/icnn_ebundle.py:105-161,337-452       Model.__init__ / Model.f        (the conv PICNN used on Olivetti)
 
 What this pins: WHICH tensor multiplies which, which layers carry a bias / an activation / a batch-norm, the
 variable naming, the unrolled recurrence and what is differentiated with respect to what -- all decided by the
@@ -15,6 +16,9 @@ reference's code as it executes.  What it cannot pin: the primitives themselves.
 the libraries' published semantics, one line each:
 
   tflearn.fully_connected(x, n, activation, bias)   x @ W [+ b], W laid out [n_in, n_units]; 'relu' / 'linear'
+  tflearn.conv_2d(x, nf, k, strides, 'same', bias)    NHWC cross-correlation, W laid out [k, k, c_in, nf]; TensorFlow 'SAME'
+                                                    padding: out = ceil(in / s), total = max((out-1) s + k - in, 0),
+                                                    floor(total / 2) before, the rest after
   tflearn.batch_normalization (is_training False)   (x - moving_mean) / sqrt(moving_variance + 1e-5) * gamma + beta
   tflearn.activations.leaky_relu(x, alpha)          relu(x) - alpha * relu(-x)
   tf.gradients(ys, xs)                              d sum(ys) / d xs  (TensorFlow sums over ys)
@@ -38,6 +42,13 @@ import torch
 
 DT = torch.float64
 BN_EPS = 1e-5        # tflearn.layers.normalization.batch_normalization(epsilon=1e-5)
+
+
+def _get_shape(self):
+    return [types.SimpleNamespace(value=int(d)) for d in self.shape]
+
+
+torch.Tensor.get_shape = _get_shape      # prevU.get_shape()[1].value (completion/icnn_ebundle.py:416); test infrastructure only
 
 
 class Variable:
@@ -149,6 +160,7 @@ class Shim:
         tf.minimum = lambda a, b: torch.minimum(_t(a), _t(b))
         tf.clip_by_value = lambda x, lo, hi: torch.clamp(_t(x), lo, hi)
         tf.stop_gradient = lambda x: _t(x).detach()
+        tf.contrib = types.SimpleNamespace(layers=types.SimpleNamespace(flatten=lambda x: _t(x).reshape(_t(x).shape[0], -1)))
 
         def _red(fn):
             def red(x, axis=None, reduction_indices=None):
@@ -196,6 +208,8 @@ class Shim:
                             regularizer=None, weight_decay=0.001, trainable=True, restore=True, reuse=False,
                             scope=None, name="FullyConnected"):
             x = _t(incoming)
+            if x.dim() > 2:                                     # tflearn flattens a conv feature map (NHWC order)
+                x = x.reshape(x.shape[0], -1)
             W = sh.get(scope.name + "/W")
             assert W.shape == (x.shape[1], n_units), (scope.name, tuple(W.shape), (x.shape[1], n_units))
             out = x @ W
@@ -218,6 +232,35 @@ class Shim:
             mu, var = sh.get(pre + "moving_mean"), sh.get(pre + "moving_variance")
             return (_t(incoming) - mu) / torch.sqrt(var + BN_EPS) * g + b
         tl.batch_normalization = batch_normalization
+
+        def conv_2d(incoming, nb_filter, filter_size, strides=1, padding="same", activation="linear", bias=True,
+                    weights_init=None, bias_init=None, regularizer=None, weight_decay=0.001, trainable=True,
+                    restore=True, reuse=False, scope=None, name="Conv2D"):
+            import torch.nn.functional as F
+            assert padding == "same"
+            x = _t(incoming)                                    # NHWC
+            st = strides if isinstance(strides, int) else strides[1]
+            assert isinstance(strides, int) or (strides[0] == 1 and strides[3] == 1 and strides[1] == strides[2])
+            k = filter_size
+            W = sh.get(scope.name + "/W")                       # [k, k, c_in, nb_filter]
+            assert W.shape == (k, k, x.shape[3], nb_filter), (scope.name, tuple(W.shape), (k, k, x.shape[3], nb_filter))
+            pads = []
+            for size in (x.shape[2], x.shape[1]):               # F.pad order: (W_before, W_after, H_before, H_after)
+                out = -(-size // st)
+                tot = max((out - 1) * st + k - size, 0)
+                pads += [tot // 2, tot - tot // 2]
+            b = None
+            if bias:
+                b = sh.get(scope.name + "/b")
+            else:
+                assert scope.name + "/b" not in sh.vars, scope.name + " is bias-free in the reference"
+            y = F.conv2d(F.pad(x.permute(0, 3, 1, 2), pads), W.permute(3, 2, 0, 1), b, stride=st).permute(0, 2, 3, 1)
+            if activation == "relu":
+                y = torch.relu(y)
+            else:
+                assert activation == "linear", activation
+            return y
+        tl.conv_2d = conv_2d
         tl.activations = types.SimpleNamespace(
             leaky_relu=lambda x, alpha=0.1: torch.relu(_t(x)) - alpha * torch.relu(-_t(x)))
         tl.is_training = lambda flag: None

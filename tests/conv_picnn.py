@@ -1,7 +1,9 @@
 """A convolutional PICNN energy in plain torch, written from completion/icnn_ebundle.py:337-452 (the
 architecture the reference actually uses on Olivetti: three conv z-layers 32x8/4, 64x4/2, 64x3/1 with
 'same' padding, then FC 512 and 1; batch-norm left out).  TEST HELPER ONLY: it plays
-the role of the USER's ``fg`` in callback mode -- the library never sees the network, only (f, g)."""
+the role of the USER's ``fg`` in callback mode -- the library never sees the network, only (f, g).
+Pinned by the reference's own Model.__init__ / Model.f executed on oracle/tf_shim.py (E_ and dE_dy_ agree to 1e-10 at the
+Olivetti dims: tests/test_oracle_tfshim.py::test_conv_picnn_helper_matches_the_reference_graph)."""
 import numpy as np
 import torch
 import torch.nn.functional as F

@@ -125,3 +125,16 @@ def test_unrolled_gd_and_training_gradient_match_the_reference_graph(tag, gold):
             if nm in gold.files:
                 assert not np.any(gold[nm])
     assert checked >= (8 * p.L + 3 if tag == "gdgrad_small" else 8)
+
+
+@pytest.mark.parametrize("tag", ["conv_small", "conv_olivetti"])
+def test_conv_picnn_helper_matches_the_reference_graph(tag, gold):
+    """tests/conv_picnn.py -- the user-side ``fg`` the GPU callback-mode test drives K2 with at the Olivetti dims
+     -- against E_ / dE_dy_ of the reference's own convolutional Model.__init__ / Model.f
+    (completion/icnn_ebundle.py:105-161,337-452) executed on oracle/tf_shim.py: same wiring (u-path convs 32x8/4,
+    64x4/2, 64x3/1 + FC 512, 1; y_red path; gates), 'SAME' padding, NHWC flatten order of the dense layers."""
+    from oracle.gen_golden_tfshim import conv_case
+    net, x, y = conv_case(tag)
+    f, g = net.make_fg(x)(y)
+    close(f, gold[tag + "_f"], "E_")
+    close(g, gold[tag + "_g"], "dE_dy_")
