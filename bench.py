@@ -92,13 +92,20 @@ def k2_fp64_flops(n, stats):
 # CPU side (oracle port) -- the only place bench.py executes oracle/
 # ------------------------------------------------------------------------------------------
 
+_WORKER_CACHE = {}      # one entry per worker process: (workload, seed, Bgen) -> (p, x, y0)
+
+
 def _cpu_worker(args):
     workload, seed, lo, hi, Bgen, nIter, dense_diag, verbose = args
     from threadpoolctl import threadpool_limits
     from oracle import bundle_np, picnn_np
     from icnn_b200 import workloads
     cfg = workloads.CONFIGS[workload]
-    p, x, y0 = workloads.make_inputs(workload, B=Bgen, seed=seed)
+    key = (workload, seed, Bgen)
+    if key not in _WORKER_CACHE:      # the pool's processes persist across steps: generate theta / inputs once (untimed
+        _WORKER_CACHE.clear()         # either way; at C5 it is 3 s and 0.4 GB per process), keep only the latest
+        _WORKER_CACHE[key] = workloads.make_inputs(workload, B=Bgen, seed=seed)
+    p, x, y0 = _WORKER_CACHE[key]
     x, y0 = x[lo:hi], y0[lo:hi].copy()
     # float32 arithmetic mimics the reference's TF-backed fg; the values are handed over in float64
     # arrays so that the CPU arm does the same work as the GPU arm: np.linalg.matrix_rank scales its

@@ -61,16 +61,18 @@ def gates(p: PicnnParams, x):
 def fg_gated(p: PicnnParams, gts, y, dtype=np.float64):
     """Energy f [B] and gradient df/dy [B, n] for iterate y [B, n] given precomputed gates.
     Forward  multi-label-cls/icnn_ebundle.py:349-387 / RL/src/icnn.py:356-404;
-    gradient = what tf.gradients(E_, y_) (:146) evaluates, written out by hand."""
+    gradient = what tf.gradients(E_, y_) (:146) evaluates, written out by hand.
+    (``np.asarray(.., dtype)`` is a no-op on operands already of ``dtype``: make_fg casts weights and gates once.)"""
     cz, cy, d = gts
-    y = np.asarray(y, dtype=dtype)
+    c = lambda a: np.asarray(a, dtype=dtype)          # noqa: E731
+    y = c(y)
     L, a = p.L, p.alpha
     zs = []
     z = None
     for i in range(L + 1):
-        pre = (y * cy[i].astype(dtype)) @ p.Wy[i].astype(dtype) + d[i].astype(dtype)
+        pre = (y * c(cy[i])) @ c(p.Wy[i]) + c(d[i])
         if i > 0:
-            pre = pre + (z * cz[i].astype(dtype)) @ p.Wz[i].astype(dtype)
+            pre = pre + (z * c(cz[i])) @ c(p.Wz[i])
         if i < L:
             z = np.where(pre > 0, pre, a * pre)
         else:
@@ -80,11 +82,21 @@ def fg_gated(p: PicnnParams, gts, y, dtype=np.float64):
     delta = np.ones_like(zs[L])
     g = np.zeros_like(y)
     for i in range(L, -1, -1):
-        g += cy[i].astype(dtype) * (delta @ p.Wy[i].astype(dtype).T)
+        g += c(cy[i]) * (delta @ c(p.Wy[i]).T)
         if i > 0:
             dact = np.where(zs[i - 1] > 0, 1.0, a).astype(dtype)
-            delta = dact * cz[i].astype(dtype) * (delta @ p.Wz[i].astype(dtype).T)
+            delta = dact * c(cz[i]) * (delta @ c(p.Wz[i]).T)
     return f, g
+
+
+class _Cast:
+    """The z-path weights of ``p`` cast to ``dtype`` once (the reference's TF graph holds float32 variables; it does
+    not convert them per sess.run)."""
+
+    def __init__(self, p, dtype):
+        self.L, self.alpha = p.L, p.alpha
+        self.Wy = [np.asarray(w, dtype=dtype) for w in p.Wy]
+        self.Wz = [None if w is None else np.asarray(w, dtype=dtype) for w in p.Wz]
 
 
 def make_fg(p: PicnnParams, x, dtype=np.float64, out_dtype=None, affine=False):
@@ -93,6 +105,9 @@ def make_fg(p: PicnnParams, x, dtype=np.float64, out_dtype=None, affine=False):
     arithmetic, ``out_dtype=np.float32`` mimics the float32 fetch.  ``affine=True`` applies the
     RL wrapper (RL/src/icnn.py:148-153): the solver variable is x in [0,1], a = 2x-1, grad *= 2."""
     gts = gates(p, x)
+    if np.dtype(dtype) != np.float64:                 # cast weights and gates once, not per call
+        gts = tuple([None if g_ is None else g_.astype(dtype) for g_ in gs] for gs in gts)
+        p = _Cast(p, dtype)
 
     def fg(y):
         yy = 2.0 * np.asarray(y) - 1.0 if affine else y
