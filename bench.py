@@ -567,6 +567,20 @@ def measure_workload(ctx, name, steps, warmup, scaling, solver, cpu_seconds, hea
     }
     if clk:
         rec["clocks"] = clk.summary()
+    # what bounds strong scaling: K2 runs one CTA per sample, ceil(rows / resident CTAs) waves per launch -- with fewer rows
+    # per GPU the last partial wave weighs more (wave quantisation); the all-gather of y* is one NCCL call per step
+    try:
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        v3 = k2_name.startswith("bundle_pc_kernel<8 warps, three n-vectors>")
+        if v3 and B > 0:
+            resident = 2 * sms
+            waves = -(-B // resident)
+            rec["strong_scaling_model"] = {
+                "limiting_kernel": "K2 " + k2_name, "resident_samples_per_gpu": resident, "rows_per_gpu": B,
+                "waves_per_launch": waves, "wave_efficiency": B / float(resident * waves),
+                "allgather_bytes_per_step": int(Bglob * n * 8) if world > 1 else 0}
+    except Exception as exc:      # informational only
+        rec["strong_scaling_model"] = {"error": repr(exc)}
     # ---- C3 (SURVEY.md 8d config 3 asks for both inner loops): 30-step momentum GD next to the bundle loop,
     # the final mean f(y) - H(y) of each (what ebundle-vs-gd.py:94-99 plots), and the GD training backward
     if name == "C3" and world == 1 and not cfg["affine"]:
@@ -664,6 +678,7 @@ def run_gpu(args):
             "clocks": head.get("clocks"), "roofline": head["roofline"], "kernels": head["kernels"],
             "cpu_baseline": head.get("cpu_baseline"), "e2e_over_cpu": head.get("e2e_over_cpu"),
             "per_iteration": head["per_iteration"], "loop_graph": head.get("loop_graph"),
+            "strong_scaling_model": head.get("strong_scaling_model"),
             "fp64_mma_peak_tflops": ctx.fp64_peak,
             "configs": subs,
             "target_shape": subs.get("T"),
