@@ -116,7 +116,7 @@ class BundleState:
         key = (id(fg.net), fg.net._pack_gen, fg.net._h.value, fg.ws.data_ptr(), fg.B,
                tuple(None if t is None else t.data_ptr() for lst in (fg.cy, fg.cz, fg.d) for t in lst),
                (fg.c_gates.in_scale, fg.c_gates.in_shift, fg.c_gates.g_scale),
-               bytes(cfg))
+               bytes(cfg), self.c.iter_stats, self.c.f64)
         g = self._graphs.get(key)
         if g is None:
             while len(self._graphs) >= self._MAX_GRAPHS:
@@ -306,6 +306,8 @@ def solveBatch(fg, initXs, nIter=None, callback=None, solver="pc", *, variant="l
         if state is not None and state.compatible(*need):
             st = state
             st.reset_views()
+            if st.iter_stats is not None:      # a reused state collects statistics (atomics) only when this call asks
+                st.c.iter_stats = st.iter_stats.data_ptr() if stats else None
         else:
             st = BundleState(B, n, KS, dev, keep_xs=keep_xs, nIter=nIter, stats=stats)
         with _nvtx("icnn:h2d"):
