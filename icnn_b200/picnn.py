@@ -125,9 +125,11 @@ class PICNN:
         return torch.empty(max(nbytes, 4), dtype=torch.uint8, device=self.device)
 
     def gates(self, x):
-        """x-path products (cz, cy, d), constant over the inner loop.  Plain library GEMMs
-        (torch.matmul -> cuBLAS): this is the once-per-solveBatch precompute, not the hot loop
-        (SURVEY.md section 8f row 2 lists a hand-written kernel for it as "next")."""
+        """x-path products (cz, cy, d), constant over the inner loop: one tcgen05 GEMM per
+        source activation with a bias / ReLU / scatter epilogue (``icnn_picnn_gates``).  Only when the library reports
+        the shape unsupported (``icnn_picnn_set_xpath`` -> ICNN_E_UNSUPPORTED, e.g. ICNN_K1=simt builds of the handle)
+        the same products are formed by library GEMMs (torch.addmm -> cuBLAS): a once-per-solveBatch precompute,
+        outside the hot loop."""
         x = _dev(x, self.device)
         L = self.L
         if self._xpath:

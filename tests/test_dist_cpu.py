@@ -91,3 +91,61 @@ def test_allreduce_grads_gloo(ws):
     for p in procs:
         p.join(timeout=60)
     assert sorted(r for r, _ in res) == list(range(ws)) and all(ok for _, ok in res)
+
+
+class _FakeNet:
+    """Stands in for a PICNN replica: ``bind`` keeps the row block it was given."""
+    device = torch.device("cpu")
+
+    def bind(self, x, affine=False):
+        return ("bound", np.asarray(x, dtype=np.float64), affine)
+
+
+def _fake_solve_batch(fg, initXs, nIter=None, solver="pc", variant="lib", return_state=False, device=None, **kw):
+    """The shape of bundle_entropy.solveBatch's result with a trivial 'solve': y = y0 + (global row id) + nIter."""
+    import types
+    y0 = initXs.numpy() if isinstance(initXs, torch.Tensor) else np.asarray(initXs)
+    if fg is None:                       # a rank that owns no rows
+        assert y0.shape[0] == 0 and device is not None
+        y = np.zeros((0, y0.shape[1]))
+    else:
+        y = y0 + fg[1][:, :1] + float(nIter)
+    st = types.SimpleNamespace(y=torch.from_numpy(np.ascontiguousarray(y)))
+    return (y, [], [], [], [], [nIter] * y.shape[0], st)
+
+
+def _worker_sharded(rank, ws, port, B, n, as_tensor, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        from icnn_b200 import bundle_entropy
+        bundle_entropy.solveBatch = _fake_solve_batch          # this process only
+        x = np.arange(B, dtype=np.float64)[:, None] * np.ones((1, 3))     # x[i, :] = global row id
+        y0 = np.random.RandomState(0).uniform(size=(B, n))
+        y0_in = torch.from_numpy(y0.copy()) if as_tensor else y0.copy()
+        y_all, local = idist.solve_batch_sharded(_FakeNet(), x, y0_in, nIter=4)
+        lo, hi = idist.shard_rows(B, rank, ws)
+        ok = (tuple(y_all.shape) == (B, n)
+              and np.allclose(y_all.numpy(), y0 + np.arange(B)[:, None] + 4.0, rtol=0, atol=0)
+              and len(local) == 6 and local[0].shape[0] == hi - lo
+              and np.array_equal(np.asarray(y0_in), y0))                 # the caller's y0 is not touched (block copies)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ws,B,as_tensor", [(2, 5, False), (2, 5, True), (3, 2, False), (3, 1, True), (2, 8, False)])
+def test_solve_batch_sharded_orchestration_gloo(ws, B, as_tensor):
+    """icnn_b200.dist.solve_batch_sharded on CPU/gloo with the device solve replaced by a stub: contiguous row
+    blocks reach the right rank, ragged and EMPTY shards (B < world size) still take part in the all-gather, numpy
+    and torch y0 are both accepted, the gathered y* is in global row order on every rank."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_sharded, args=(r, ws, port, B, 4, as_tensor, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(ws)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r for r, _ in res) == list(range(ws)) and all(ok for _, ok in res), res
