@@ -52,3 +52,22 @@ def test_cuda_arm_fails_loudly_without_a_gpu():
                           "--warmup", "1", "--no-cpu-baseline"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode != 0
     assert not [l for l in out.stdout.splitlines() if l.startswith("{")]      # no number without a device
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """The driver launches the reference arm like the CUDA arm at N > 1 (torchrun, one rank per GPU): rank 0 alone
+    runs the CPU path and prints the line, the other ranks exit 0 without work."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--workload", "C1", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["native_modules_loaded"] == []
