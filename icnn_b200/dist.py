@@ -55,7 +55,18 @@ def solve_batch_sharded(net, x, y0, nIter=None, solver="pc", variant="lib", affi
     B = x.shape[0]
     lo, hi = shard_rows(B, rank, ws)
     y0b = y0[lo:hi]
-    y0b = y0b.clone() if isinstance(y0b, torch.Tensor) else np.array(y0b, dtype=np.float64)
+    if isinstance(y0b, torch.Tensor):
+        # solveBatch overwrites its initXs in place: work on a copy of this rank's block, pinned when the caller's
+        # batch is (the H2D of y0 and the D2H of y* then run at the pinned-memory rate)
+        blk = None
+        if y0b.is_pinned():
+            try:
+                blk = torch.empty_like(y0b, pin_memory=True).copy_(y0b)
+            except RuntimeError:
+                blk = None
+        y0b = blk if blk is not None else y0b.clone()
+    else:
+        y0b = np.array(y0b, dtype=np.float64)
     if hi > lo:
         fg = net.bind(x[lo:hi], affine=affine)
         out = bundle_entropy.solveBatch(fg, y0b, nIter=nIter, solver=solver, variant=variant,
