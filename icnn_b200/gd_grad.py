@@ -105,9 +105,10 @@ def _xpath_backward(net, x, dcy, dcz):
     return out
 
 
-def make_cvx(Wz, halve=False):
+def make_cvx(Wz, halve=False, divide=None):
     """``makeCvx``: W <- |W| (multi-label-cls/icnn-back.py:143), |W|/2 with ``halve``
-    (completion/icnn.back.py:164), for every 'proj' weight Wz[1..L]; in place on torch tensors.
+    (completion/icnn.back.py:164, completion/icnn_ebundle.py:145), |W|/``divide`` in general
+    (synthetic-cls/icnn.py:145 uses 10), for every 'proj' weight Wz[1..L]; in place on torch tensors.
     When applied to a PICNN's own tensors (``make_cvx(net.Wz)``) follow with ``net.update_weights()``: the
     device library works on packed copies, and ``net.bind`` refuses to run on stale ones."""
     for w in Wz:
@@ -115,6 +116,8 @@ def make_cvx(Wz, halve=False):
             w.abs_()
             if halve:
                 w.mul_(0.5)
+            if divide is not None:
+                w.div_(float(divide))
     return Wz
 
 

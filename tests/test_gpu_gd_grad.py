@@ -193,6 +193,7 @@ def test_make_cvx_and_proj():
     np.testing.assert_array_equal(proj([None, w[1].clone()])[1].numpy(), [[0, 2], [0.5, 0]])
     np.testing.assert_array_equal(make_cvx([None, w[1].clone()])[1].numpy(), [[1, 2], [0.5, 4]])
     np.testing.assert_array_equal(make_cvx([None, w[1].clone()], halve=True)[1].numpy(), [[0.5, 1], [0.25, 2]])
+    np.testing.assert_allclose(make_cvx([None, w[1].clone()], divide=10)[1].numpy(), [[0.1, 0.2], [0.05, 0.4]], rtol=1e-6)
 
 
 def test_in_place_weight_updates_must_be_repacked():
