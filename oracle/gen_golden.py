@@ -75,7 +75,8 @@ def pack_ragged(lst, kmax, inner_shape, dtype=np.float64):
     return out
 
 
-def run_case(name, cfgname, B, nIter, variant, solver):
+def compute_case(name, cfgname, B, nIter, variant, solver):
+    """-> (arrays of the golden file, seconds, counts, nIters): the UNMODIFIED reference module run on the seeded case."""
     cfg = synth.CONFIGS[cfgname]
     p, x, y0 = synth.make_inputs(cfgname, B=B)
     fg = picnn_np.make_fg(p, x, affine=cfg["affine"])
@@ -105,6 +106,11 @@ def run_case(name, cfgname, B, nIter, variant, solver):
     if n <= 512:  # keep fixtures small: rows / iterates only for the small shapes
         out["A"] = pack_ragged(A, kmax, (n,))
         out["xs"] = pack_ragged(xs, kmax, (n,))
+    return out, dt, counts, nIters
+
+
+def run_case(name, cfgname, B, nIter, variant, solver):
+    out, dt, counts, nIters = compute_case(name, cfgname, B, nIter, variant, solver)
     path = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(path, **out)
     print("%-12s %-3s B=%-4d nIter=%-3d %-4s  %.1fs  k mean %.2f max %d  nIters mean %.2f  -> %s (%d KB)" % (

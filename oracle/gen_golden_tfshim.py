@@ -274,7 +274,8 @@ def run_completion_model(tag):
     return model.E_.detach().numpy(), model.dE_dyFlat_.detach().numpy(), len(sh.created)
 
 
-def main():
+def generate():
+    """-> {name: array}: every golden of tests/golden/picnn_tfshim.npz, recomputed from /root/reference."""
     sys.path.insert(0, os.path.join(REF, "RL", "src"))
     from oracle.gen_golden import _load
     out = {}
@@ -334,6 +335,11 @@ def main():
         out[tag + "_f"], out[tag + "_g"], nv = run_completion_model(tag)
         print(tag, "variables", nv, "f", out[tag + "_f"])
 
+    return out
+
+
+def main():
+    out = generate()
     path = os.path.join(ROOT, "tests", "golden", "picnn_tfshim.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, len(out), "arrays,", os.path.getsize(path) // 1024, "KB")

@@ -128,3 +128,21 @@ def test_adam_restatement_matches_reference_body(golden_dir):
     best, its = adam_np.adam(adam_np.make_fg_entr(p, x), x, p.n)
     assert its == int(gold["c4_iters"])
     np.testing.assert_allclose(best, gold["c4_act_best"], atol=1e-12)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/lib"), reason="needs the reference checkout (build container only)")
+@pytest.mark.parametrize("case", ["c1_pc", "c1_dual", "c1_rl", "c1_boyd", "c4_rl"])
+def test_committed_goldens_regenerate_from_the_reference(case, golden_dir):
+    """Run the unmodified reference module again (the build container holds /root/reference; the GPU box does not
+    and skips this) and compare with the committed file: the goldens are the reference's output, bit for bit."""
+    from oracle import gen_golden
+    spec = [c for c in gen_golden.CASES if c[0] == case][0]
+    fresh = gen_golden.compute_case(*spec)[0]
+    gold = np.load(os.path.join(golden_dir, case + ".npz"))
+    assert sorted(fresh) == sorted(gold.files)
+    for k in gold.files:
+        a, b = np.asarray(fresh[k]), gold[k]
+        if b.dtype.kind in "US":
+            assert str(a) == str(b), k
+        else:
+            np.testing.assert_array_equal(a, b, err_msg=k)
