@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from .picnn import BoundPICNN
+from .picnn import BoundPICNN, default_device
 
 __all__ = ["solveBatch", "solve", "BundleState", "VARIANT_DEFAULTS"]
 
@@ -280,7 +280,7 @@ def solveBatch(fg, initXs, nIter=None, callback=None, solver="pc", *, variant="l
     if not torch.cuda.is_available():
         raise RuntimeError("icnn_b200.solveBatch needs a CUDA device (no CPU fallback)")
     fused = isinstance(fg, BoundPICNN)
-    dev = fg.net.device if fused else torch.device(device if device is not None else "cuda")
+    dev = fg.net.device if fused else (torch.device(device) if device is not None else default_device())
     x0 = initXs
     B, n = x0.shape
     if B == 0 or nIter < 1:

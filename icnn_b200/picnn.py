@@ -15,6 +15,17 @@ import torch
 from . import _capi
 
 
+def default_device():
+    """Device used when the caller names none: ``cuda`` (torch's current device), or -- the device-list environment
+    variable of SURVEY.md section 5 -- entry LOCAL_RANK of ``ICNN_DEVICES`` (comma-separated CUDA ordinals, e.g.
+    ``ICNN_DEVICES=4,5,6,7`` under torchrun with four ranks, or a single ordinal for a single process)."""
+    import os
+    lst = [s for s in os.environ.get("ICNN_DEVICES", "").split(",") if s.strip()]
+    if lst:
+        return torch.device("cuda", int(lst[int(os.environ.get("LOCAL_RANK", "0")) % len(lst)]))
+    return torch.device("cuda")
+
+
 def _dev(a, device):
     if isinstance(a, torch.Tensor):
         return a.to(device=device, dtype=torch.float32).contiguous()
@@ -35,7 +46,7 @@ class PICNN:
                  device=None):
         if not torch.cuda.is_available():
             raise RuntimeError("icnn_b200.PICNN needs a CUDA device (no CPU fallback)")
-        self.device = torch.device(device if device is not None else "cuda")
+        self.device = torch.device(device) if device is not None else default_device()
         self.m, self.n, self.hidden, self.alpha = int(m), int(n), [int(s) for s in hidden], float(alpha)
         self.L = len(self.hidden)
         L = self.L

@@ -75,3 +75,19 @@ def test_dropin_module_names_exist():
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         assert callable(mod.solveBatch)
+
+
+def test_device_list_environment_variable(monkeypatch):
+    """ICNN_DEVICES ("env var for device list"): entry LOCAL_RANK of the list, else torch's current device."""
+    import torch
+    from icnn_b200.picnn import default_device
+    monkeypatch.delenv("ICNN_DEVICES", raising=False)
+    assert default_device() == torch.device("cuda")
+    monkeypatch.setenv("ICNN_DEVICES", "4,5,6,7")
+    monkeypatch.setenv("LOCAL_RANK", "2")
+    assert default_device() == torch.device("cuda", 6)
+    monkeypatch.delenv("LOCAL_RANK")
+    assert default_device() == torch.device("cuda", 4)
+    monkeypatch.setenv("ICNN_DEVICES", "3")
+    monkeypatch.setenv("LOCAL_RANK", "5")
+    assert default_device() == torch.device("cuda", 3)
