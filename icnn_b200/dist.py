@@ -61,8 +61,8 @@ def solve_batch_sharded(net, x, y0, nIter=None, solver="pc", variant="lib", affi
         blk = None
         if y0b.is_pinned():
             try:
-                blk = torch.empty_like(y0b, pin_memory=True).copy_(y0b)
-            except RuntimeError:
+                blk = torch.empty(tuple(y0b.shape), dtype=y0b.dtype, pin_memory=True).copy_(y0b)
+            except Exception:      # no pinned memory to be had: a pageable copy is still correct
                 blk = None
         y0b = blk if blk is not None else y0b.clone()
     else:
