@@ -91,3 +91,20 @@ def test_device_list_environment_variable(monkeypatch):
     monkeypatch.setenv("ICNN_DEVICES", "3")
     monkeypatch.setenv("LOCAL_RANK", "5")
     assert default_device() == torch.device("cuda", 3)
+
+
+def test_plain_c_consumer_compiles_and_links_without_a_gpu(tmp_path):
+    """include/icnn_b200.h is valid C99 (no C++-isms, no torch types) and tests/c_abi/smoke.c -- the plain-C consumer
+    the GPU suite runs -- compiles and links against libicnn_b200.so here (it is executed on the GPU box only)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr_only = tmp_path / "hdr.c"
+    hdr_only.write_text('#include "icnn_b200.h"\nint main(void) { return ICNN_ABI_VERSION > 0 ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                           "-c", str(hdr_only), "-o", str(tmp_path / "hdr.o")])
+    lib = os.path.join(root, "icnn_b200")
+    subprocess.check_call(["gcc", "-O1", "-std=c99", "-I", os.path.join(root, "include"), "-I", "/usr/local/cuda/include",
+                           os.path.join(root, "tests", "c_abi", "smoke.c"), "-o", str(tmp_path / "smoke"),
+                           "-L", lib, "-l:libicnn_b200.so", "-L", "/usr/local/cuda/lib64", "-lcudart", "-lm",
+                           "-Wl,-rpath," + lib + ":/usr/local/cuda/lib64"])
+    assert (tmp_path / "smoke").exists()
