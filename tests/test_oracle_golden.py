@@ -130,6 +130,7 @@ def test_adam_restatement_matches_reference_body(golden_dir):
     np.testing.assert_allclose(best, gold["c4_act_best"], atol=1e-12)
 
 
+@pytest.mark.filterwarnings("ignore")      # the reference runs under np.seterr(all='warn') and warns freely
 @pytest.mark.skipif(not os.path.isdir("/root/reference/lib"), reason="needs the reference checkout (build container only)")
 @pytest.mark.parametrize("case", ["c1_pc", "c1_dual", "c1_rl", "c1_boyd", "c4_rl"])
 def test_committed_goldens_regenerate_from_the_reference(case, golden_dir):
