@@ -71,3 +71,22 @@ def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
     assert len(lines) == 1, out.stdout[-2000:]
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["native_modules_loaded"] == []
+
+
+def test_algorithmic_work_models_match_survey_8d():
+    """The roofline numerators: FLOP_fg = 4 * MAC per solve (C2 9.45 M, C3 0.866 M, C4 0.170 M,
+    C5 79.7 M, T 8.39 M) and the K2 FP64 model n (k^2 + 11 k + 30) per interior-point iteration."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from icnn_b200 import workloads
+    want = {"C1": 4 * 536, "C2": 4 * 2361856, "C3": 4 * 216399, "C4": 4 * 42606, "C5": 4 * 19928064, "T": 4 * 2098688}
+    for name, flops in want.items():
+        assert bench.flop_fg(workloads.CONFIGS[name]) == float(flops), name
+    # one sample, one iteration entered, 3 interior-point iterations with k = 5 rows, n = 100
+    stats = np.zeros((1, 8))
+    stats[0, 2], stats[0, 3], stats[0, 4] = 3, 3 * 25, 3 * 5
+    assert bench.k2_fp64_flops(100, stats) == 100.0 * 3 * (25 + 55 + 30)
+    assert bench.workload_string("T", workloads.CONFIGS["T"]).startswith("T: m=512 n_y=512 hidden=[1024, 1024] batch=4096 nIter=10")
