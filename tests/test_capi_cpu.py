@@ -108,3 +108,37 @@ def test_plain_c_consumer_compiles_and_links_without_a_gpu(tmp_path):
                            "-L", lib, "-l:libicnn_b200.so", "-L", "/usr/local/cuda/lib64", "-lcudart", "-lm",
                            "-Wl,-rpath," + lib + ":/usr/local/cuda/lib64"])
     assert (tmp_path / "smoke").exists()
+
+
+def test_ragged_result_views_follow_perm_and_count():
+    """Host logic of the 6-tuple: A / b / lam / xs are lazy list-of-lists views over the dense slot buffers, in the
+    sample's LOGICAL order (perm maps logical index -> physical slot; pruning permutes perm only).  Exercised on CPU
+    tensors -- BundleState only stores pointers, no kernel runs."""
+    import torch
+    from icnn_b200.bundle_entropy import BundleState, _Rows
+    B, n, KS = 3, 4, 5
+    st = BundleState(B, n, KS, torch.device("cpu"), keep_xs=True, nIter=4)
+    st.G.copy_(torch.arange(B * KS * n, dtype=torch.float32).reshape(B, KS, n))
+    st.ys.copy_(-torch.arange(B * KS * n, dtype=torch.float64).reshape(B, KS, n))
+    st.h.copy_(torch.arange(B * KS, dtype=torch.float64).reshape(B, KS) * 0.5)
+    st.lam.copy_(torch.arange(B * KS, dtype=torch.float64).reshape(B, KS) * 0.25)
+    st.perm.copy_(torch.tensor([[3, 0, 1, 2, 4], [4, 3, 2, 1, 0], [0, 1, 2, 3, 4]], dtype=torch.int32))
+    st.count.copy_(torch.tensor([2, 0, 4], dtype=torch.int32))
+    A, b, lam, xs = (_Rows(st, k) for k in ("A", "b", "lam", "xs"))
+    assert len(A) == B and [len(a) for a in A] == [2, 0, 4]                      # nActive = len(G[j])
+    np.testing.assert_array_equal(np.array(A[0]), st.G[0, [3, 0]].numpy())        # logical order = perm order
+    np.testing.assert_array_equal(np.array(xs[0]), st.ys[0, [3, 0]].numpy())
+    assert b[0] == [0.5 * 3, 0.0] and A[1] == [] and b[1] == [] and lam[1] is None and xs[1] == []
+    np.testing.assert_array_equal(lam[2], st.lam[2, :4].numpy())
+    assert isinstance(A[2][1], np.ndarray) and A[2][1].shape == (n,) and A[-1] is A[2]
+    assert [len(a) for a in A[0:2]] == [2, 0]
+    import pytest
+    with pytest.raises(IndexError):
+        A[3]
+    st2 = BundleState(B, n, KS, torch.device("cpu"), keep_xs=False, nIter=4)
+    st2.count.fill_(1)
+    st2.perm.copy_(st.perm)
+    with pytest.raises(RuntimeError):
+        _Rows(st2, "xs")[0]
+    assert st.compatible(B, n, KS, torch.device("cpu"), True, 3, False, False) and not st.compatible(B, n, KS + 1, torch.device("cpu"), True, 3, False, False)
+    assert not st.compatible(B, n, KS, torch.device("cpu"), True, 9, False, False)      # more iterations than nactive holds
