@@ -142,3 +142,22 @@ def test_ragged_result_views_follow_perm_and_count():
         _Rows(st2, "xs")[0]
     assert st.compatible(B, n, KS, torch.device("cpu"), True, 3, False, False) and not st.compatible(B, n, KS + 1, torch.device("cpu"), True, 3, False, False)
     assert not st.compatible(B, n, KS, torch.device("cpu"), True, 9, False, False)      # more iterations than nactive holds
+
+
+def test_solver_configuration_mirrors_the_three_reference_copies():
+    """_make_cfg: defaults of lib / dual / RL copies (nIter 10/10/5, line search on/off/on, prune thresholds 1e-8/0/0),
+    'boyd' accepted, an unknown solver raises the reference's message (lib/bundle_entropy.py:232)."""
+    import pytest
+    from icnn_b200 import _capi
+    from icnn_b200.bundle_entropy import VARIANT_DEFAULTS, _make_cfg
+    assert [VARIANT_DEFAULTS[v]["nIter"] for v in ("lib", "dual", "rl")] == [10, 10, 5]
+    c = _make_cfg("lib", "pc", 10, None, None, 0, 159, 11)
+    assert (c.variant, c.solver, c.line_search, c.nIter) == (_capi.VARIANT["lib"], _capi.SOLVER_PC, 1, 10) and c.prune_thr == 1e-8
+    assert abs(c.rank_tol - 16.0 * 159 * np.finfo(np.float64).eps) < 1e-30
+    assert _make_cfg("lib", "boyd", 10, None, None, 0, 8, 9).solver == _capi.SOLVER_NEWTON
+    d = _make_cfg("dual", "newton", 10, None, None, 0, 8, 9)
+    assert (d.variant, d.solver, d.line_search, d.prune_thr) == (_capi.VARIANT["dual"], _capi.SOLVER_NEWTON, 0, 0.0)
+    r = _make_cfg("rl", "newton", 5, None, 1e-3, 7, 6, 6)
+    assert (r.variant, r.line_search, r.max_inner, r.rank_tol) == (_capi.VARIANT["rl"], 1, 7, 1e-3)
+    with pytest.raises(RuntimeError, match="Solver unknown: foo"):
+        _make_cfg("lib", "foo", 10, None, None, 0, 8, 9)
