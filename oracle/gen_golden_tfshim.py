@@ -256,7 +256,7 @@ def conv_variables(net):
 
 
 def run_completion_model(tag):
-    from oracle.tf_shim import Shim
+    from oracle.tf_shim import Shim, tensor_get_shape
     net, x, y = conv_case(tag)
     B, H, W, _ = CONV_CASES[tag]
     sh = Shim(conv_variables(net))
@@ -268,7 +268,7 @@ def run_completion_model(tag):
         sh.feed(k, a, requires_grad=rg)
     ns = extract(os.path.join(REF, "completion/icnn_ebundle.py"), ["Model"],
                  {"tf": sh.tf, "tflearn": sh.tflearn, "np": np, "variable_summaries": lambda *a, **k: None})
-    with contextlib.redirect_stdout(io.StringIO()):
+    with contextlib.redirect_stdout(io.StringIO()), tensor_get_shape():
         model = ns["Model"]([H, W, 1], [H, W, 1], None)
     assert not sh.unused_variables(), sh.unused_variables()
     return model.E_.detach().numpy(), model.dE_dyFlat_.detach().numpy(), len(sh.created)

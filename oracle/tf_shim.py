@@ -44,11 +44,15 @@ DT = torch.float64
 BN_EPS = 1e-5        # tflearn.layers.normalization.batch_normalization(epsilon=1e-5)
 
 
-def _get_shape(self):
-    return [types.SimpleNamespace(value=int(d)) for d in self.shape]
-
-
-torch.Tensor.get_shape = _get_shape      # prevU.get_shape()[1].value (completion/icnn_ebundle.py:416); test infrastructure only
+@contextlib.contextmanager
+def tensor_get_shape():
+    """While active, torch tensors answer ``t.get_shape()[i].value`` like TensorFlow tensors
+    (completion/icnn_ebundle.py:416 asks ``prevU.get_shape()[1].value``); removed again on exit."""
+    torch.Tensor.get_shape = lambda self: [types.SimpleNamespace(value=int(d)) for d in self.shape]
+    try:
+        yield
+    finally:
+        del torch.Tensor.get_shape
 
 
 class Variable:
