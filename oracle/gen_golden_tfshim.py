@@ -155,7 +155,6 @@ def extract(path, names, namespace):
 def _shim(c, feeds, prefix=""):
     from oracle.tf_shim import Shim
     sh = Shim(variables_from_params(c["p"], c.get("bnvars"), prefix))
-    sh.tf.trainable_variables = lambda: [sh.vars[k] for k in sh.created if "moving_" not in k]   # creation order, as TF
     for k, (a, rg) in feeds.items():
         sh.feed(k, a, requires_grad=rg)
     return sh
@@ -260,7 +259,6 @@ def run_completion_model(tag):
     net, x, y = conv_case(tag)
     B, H, W, _ = CONV_CASES[tag]
     sh = Shim(conv_variables(net))
-    sh.tf.trainable_variables = lambda: [sh.vars[k] for k in sh.created if "moving_" not in k]
     rs = np.random.RandomState(5)
     for k, a, rg in (("x", x.reshape(B, H, W, 1), False), ("y", y.reshape(B, H, W, 1), True),
                      ("trueY", np.zeros((B, H, W, 1)), False), ("v", rs.randn(B, H * W), False), ("c", rs.randn(B), False),

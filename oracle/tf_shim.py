@@ -91,9 +91,8 @@ class Shim:
     """One instance = one "default graph": variable store, feeds, scope stack, and the two module objects
     ``tf`` / ``tflearn`` to put in the namespace the reference code is exec'd in."""
 
-    def __init__(self, variables, feeds=None, trainable_order=None):
+    def __init__(self, variables, feeds=None):
         self.vars = {k: Variable(k, v) for k, v in variables.items()}
-        self.order = list(trainable_order) if trainable_order is not None else list(self.vars)
         self.feeds = dict(feeds or {})
         self.stack = [_Scope("")]
         self.created = []               # variable names in the order the reference code first asked for them
@@ -183,7 +182,8 @@ class Shim:
             return list(g)
         tf.gradients = gradients
 
-        tf.trainable_variables = lambda: [sh.vars[k] for k in sh.order]
+        # TensorFlow lists trainable variables in creation order; batch-norm moving statistics are not trainable
+        tf.trainable_variables = lambda: [sh.vars[k] for k in sh.created if "/moving_" not in k]
         noop = lambda *a, **k: None     # noqa: E731
         tf.summary = types.SimpleNamespace(scalar=noop, histogram=noop, merge_all=noop, FileWriter=noop)
         tf.scalar_summary = tf.histogram_summary = tf.merge_all_summaries = noop
