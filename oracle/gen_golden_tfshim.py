@@ -87,6 +87,9 @@ def case_inputs(tag):
     elif tag == "rl_act_c4":         # Agent.bundle_entropy end to end (reference solveBatch on the reference negQ)
         p, x, y0 = workloads.make_inputs("C4", B=48)
         c.update(p=p, x=x, y=y0)
+    elif tag == "trace_c3":          # ebundle-vs-gd.py:84-107: nSamples = 10 rows, 10 bundle iterations, callback trace of mean(f - H)
+        p, x, y0 = workloads.make_inputs("C3", B=10)
+        c.update(p=p, x=x, y=y0, layerSizes=[600], nIter=10)
     elif tag == "gd_c3":             # the case of test_momentum_gd_matches_oracle[C3-50-0.01-0.3] (script defaults)
         p, x, y0 = workloads.make_inputs("C3", B=50)
         c.update(p=p, x=x, y=y0, layerSizes=[600], lr=0.01, momentum=0.3, nIter=30,
@@ -113,7 +116,7 @@ def hash_tag(tag):
     return sum((i + 1) * ord(ch) for i, ch in enumerate(tag)) * 7919
 
 
-CASES = ["ml_fg_c3", "ml_fg_bn", "rl_fg_c4", "rl_fg_entr_c4", "rl_act_c4", "gd_c3", "gdgrad_small"]
+CASES = ["ml_fg_c3", "ml_fg_bn", "rl_fg_c4", "rl_fg_entr_c4", "rl_act_c4", "trace_c3", "gd_c3", "gdgrad_small"]
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -307,6 +310,26 @@ def generate():
     with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
         out["rl_act_c4_act"] = agent.bundle_entropy(func, c["x"])
     print("rl_act_c4 act[0]", out["rl_act_c4_act"][0])
+
+    # ---- the reference's own benchmark of the inner loop (multi-label-cls/ebundle-vs-gd.py:84-107): its Model graph as fg,
+    # its lib/bundle_entropy.solveBatch, its entr(), and the callback (t, es, x) -> mean(es - entr(x)) it plots
+    c = case_inputs("trace_c3")
+    ref_pc = _load("ref_pc_trace", os.path.join(REF, "lib/bundle_entropy.py"))
+    entr = extract(os.path.join(REF, "multi-label-cls/ebundle-vs-gd.py"), ["entr"], {"np": np})["entr"]
+    trace, iters = [], []
+
+    def fg_ref(yhats):                       # sess.run([model.E_, model.dE_dy_]) (:88-91)
+        cc = dict(c, y=np.asarray(yhats, dtype=np.float64))
+        _sh, model = run_multilabel_model(cc, os.path.join(REF, "multi-label-cls/icnn_ebundle.py"), (list(c["layerSizes"]),))
+        return model.E_.detach().numpy().copy(), model.dE_dy_.detach().numpy().copy()
+
+    def cb(iterNum, es, x):                  # :93-98
+        iters.append(iterNum)
+        trace.append(np.mean(es - entr(x)))
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+        r = ref_pc.solveBatch(fg_ref, c["y"].copy(), nIter=c["nIter"], callback=cb)
+    out["trace_c3_iters"], out["trace_c3_f_minus_H"], out["trace_c3_yN"] = np.array(iters), np.array(trace), r[0]
+    print("trace_c3 mean(f - H) per iteration:", np.round(trace, 3))
 
     # ---- multi-label Model (back-optimisation script): unrolled momentum GD and its training gradient ----------
     for tag in ("gd_c3", "gdgrad_small"):

@@ -86,6 +86,25 @@ def test_rl_action_selection_end_to_end(gold, golden_dir):
         assert np.median(err) < 1e-12 and err.max() < 1e-6 and (err > 1e-9).mean() <= 0.15, np.sort(err)[-6:]
 
 
+def test_callback_trace_of_the_reference_benchmark(gold):
+    """multi-label-cls/ebundle-vs-gd.py:84-107 run by the generator with the reference's own pieces (Model graph as fg,
+    lib/bundle_entropy.solveBatch, entr(), callback (t, es, x) -> mean(es - entr(x))): the oracle pair reproduces the
+    plotted trace and y* -- the callback contract (a12: called with the batch's f and the live iterate before the
+    per-sample loop, lib/bundle_entropy.py:208-209)."""
+    c = case_inputs("trace_c3")
+    seen, trace = [], []
+
+    def cb(t, es, x):
+        seen.append(t)
+        trace.append(float(np.mean(es - picnn_np.entr(x))))
+    with np.errstate(all="ignore"):
+        y = bundle_np.solve_batch(picnn_np.make_fg(c["p"], c["x"]), c["y"].copy(), nIter=c["nIter"], callback=cb)[0]
+    assert seen == list(gold["trace_c3_iters"])
+    np.testing.assert_allclose(trace, gold["trace_c3_f_minus_H"], rtol=0, atol=1e-9)
+    assert np.abs(y - gold["trace_c3_yN"]).max() < 1e-9
+    assert trace[-1] < trace[0]                              # the bundle method descends the entropy-regularised objective
+
+
 GRAD_KEYS = {"u%d__W": ("x", "dWu"), "u%d__b": ("x", "dbu"), "z%d_zu_u__W": ("x", "dWzu"), "z%d_zu_u__b": ("x", "dbzu"),
              "z%d_yu_u__W": ("x", "dWyu"), "z%d_yu_u__b": ("x", "dbyu"), "z%d_zu_proj__W": ("g", "dWz"),
              "z%d_yu__W": ("g", "dWy")}
